@@ -1,0 +1,131 @@
+"""Generate golden vectors by executing the REFERENCE module (build container only).
+
+Run here (where /root/reference exists):   python tests/golden/make_golden.py
+The GPU box has no /root/reference; tests only read the committed ``*.npz`` files.
+
+For every case the reference ``src/models/Hang2020.py`` module is instantiated, loaded
+with the seeded parameter table from ``oracle.hang2020_oracle.init_params`` (numpy
+PCG64, independent of the torch RNG), run on ``make_inputs`` crops, and its outputs,
+loss, gradients and BatchNorm buffers are stored.  Large gradient tensors are stored
+as a fixed strided sample plus sum / abs-sum / l2 so the fixtures stay small.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import hang2020_oracle as orc  # noqa: E402
+
+REF = "/root/reference/src/models/Hang2020.py"
+SAMPLE = 2048
+
+# name, kind, bands, classes, batch, dist, regime, training, perturb_bn, seed
+CASES = [
+    ("cfg1_vanilla_b3_c2_train", "vanilla", 3, 2, 4, "uniform", "R1", True, False, 1),
+    ("cfg1_vanilla_b3_c2_eval", "vanilla", 3, 2, 4, "uniform", "R1", False, True, 2),
+    ("hang_b3_c10_randn_train_R1", "hang2020", 3, 10, 20, "normal", "R1", True, False, 3),
+    ("hang_b3_c10_randn_train_R2", "hang2020", 3, 10, 20, "normal", "R2", True, True, 4),
+    ("hang_b369_c50_train_R1", "hang2020", 369, 50, 8, "uniform", "R1", True, False, 5),
+    ("hang_b369_c50_train_R2", "hang2020", 369, 50, 8, "uniform", "R2", True, True, 6),
+    ("hang_b369_c50_eval_R2", "hang2020", 369, 50, 8, "normal", "R2", False, True, 7),
+    ("spectral_b369_c20_train_R2", "spectral", 369, 20, 8, "uniform", "R2", True, False, 8),
+    ("spectral_b349_c10_eval_R1", "spectral", 349, 10, 5, "uniform", "R1", False, True, 9),
+    ("spatial_b349_c10_train_R2", "spatial", 349, 10, 6, "normal", "R2", True, True, 10),
+    ("vanilla_b369_c10_train", "vanilla", 369, 10, 7, "normal", "R1", True, True, 11),
+]
+
+
+def load_reference():
+    spec = importlib.util.spec_from_file_location("ref_Hang2020", REF)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def sample_index(n):
+    if n <= SAMPLE:
+        return np.arange(n)
+    return np.unique(np.linspace(0, n - 1, SAMPLE).astype(np.int64))
+
+
+def run_case(ref, case):
+    name, kind, bands, classes, batch, dist, regime, training, perturb, seed = case
+    table = orc.init_params(kind, bands, classes, seed, perturb_bn=perturb)
+    x, y = orc.make_inputs(batch, bands, classes, seed, dist)
+    cls = {"hang2020": ref.Hang2020, "spectral": ref.spectral_network,
+           "spatial": ref.spatial_network, "vanilla": ref.vanilla_CNN}[kind]
+    m = cls(bands, classes)
+    m.load_state_dict(table, strict=True)
+    m.train(training)
+    if kind == "hang2020":
+        # every head, via the sub-networks on the reference model (SURVEY 0.3 regime R2)
+        spec = m.spectral_network(x)
+        spat = m.spatial_network(x)
+        w = torch.sigmoid(m.alpha)
+        heads = spec + spat
+        result = spec[-1] * w + spat[-1] * (1 - w)
+        if regime == "R1":
+            # the reference regime must go through Hang2020.forward itself; redo on a
+            # fresh copy so BN buffers are stepped exactly once
+            m = cls(bands, classes)
+            m.load_state_dict(table, strict=True)
+            m.train(training)
+            result = m(x)
+            with torch.no_grad():
+                m2 = cls(bands, classes)
+                m2.load_state_dict(table, strict=True)
+                m2.train(training)
+                heads = m2.spectral_network(x) + m2.spatial_network(x)
+    elif kind == "vanilla":
+        result = m(x)
+        heads = [result]
+    else:
+        heads = m(x)
+        result = heads
+    loss = orc.loss_regime(regime, result, heads, y)
+    loss.backward()
+    out = {"loss": loss.detach().numpy()}
+    res = result[-1] if isinstance(result, list) else result
+    out["result"] = res.detach().numpy()
+    for i, h in enumerate(heads):
+        out[f"head{i}"] = h.detach().numpy()
+    sd = m.state_dict()
+    for k, v in sd.items():
+        if orc.is_buffer(k):
+            out[f"buf/{k}"] = v.detach().numpy()
+    for k, prm in m.named_parameters():
+        if prm.grad is None:
+            out[f"gradnone/{k}"] = np.array(1, dtype=np.int8)
+            continue
+        g = prm.grad.detach().numpy().reshape(-1)
+        idx = sample_index(g.size)
+        out[f"grad/{k}/sample"] = g[idx]
+        g64 = g.astype(np.float64)
+        out[f"grad/{k}/stats"] = np.array([g64.sum(), np.abs(g64).sum(), np.sqrt((g64 * g64).sum())])
+    return name, out
+
+
+def main():
+    torch.set_num_threads(8)
+    ref = load_reference()
+    meta = []
+    for case in CASES:
+        name, out = run_case(ref, case)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        meta.append(case)
+        print(name, "loss", float(out["loss"]), "keys", len(out))
+    with open(os.path.join(HERE, "cases.json"), "w") as f:
+        import json
+        json.dump({"torch": torch.__version__, "reference": "weecology/DeepTreeAttention@cae13f1",
+                   "fields": ["name", "kind", "bands", "classes", "batch", "dist", "regime",
+                              "training", "perturb_bn", "seed"],
+                   "cases": meta}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,44 @@
+"""CPU: the oracle restatement against golden vectors produced by the reference module
+(tests/golden/make_golden.py).  Tolerances: forward 2e-6 abs (same ATen kernels, same
+order), loss 1e-6, grads 1e-4 relative to the tensor's max."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import hang2020_oracle as orc
+
+
+@pytest.mark.parametrize("case", gu.cases(), ids=lambda c: c["name"])
+def test_oracle_matches_reference_golden(case):
+    torch.set_num_threads(8)
+    gold = gu.load(case)
+    table, x, y = gu.build(case)
+    loss, result, heads, grads, buffers = orc.step(case["kind"], table, x, y, regime=case["regime"],
+                                                   training=case["training"])
+    res = result[-1] if isinstance(result, list) else result
+    np.testing.assert_allclose(res.detach().numpy(), gold["result"], rtol=0, atol=2e-6)
+    for i, h in enumerate(heads):
+        np.testing.assert_allclose(h.detach().numpy(), gold[f"head{i}"], rtol=0, atol=2e-6)
+    assert abs(float(loss) - float(gold["loss"])) < 1e-5
+    for k, v in buffers.items():
+        np.testing.assert_allclose(v.numpy(), gold[f"buf/{k}"], rtol=1e-6, atol=1e-7)
+    gu.check_grads(gold, grads, rtol=1e-4, atol=1e-6)
+
+
+def test_param_table_matches_appendix_d():
+    names = [n for n, _, _ in orc.param_shapes("hang2020", 369, 50)]
+    assert len(names) == 85 and names[0] == "alpha"
+    total = sum(int(np.prod(s)) for n, s, r in orc.param_shapes("hang2020", 369, 50)
+                if not orc.is_buffer(n))
+    assert total == 731836
+    total_v = sum(int(np.prod(s)) for n, s, r in orc.param_shapes("vanilla", 3, 2)
+                  if not orc.is_buffer(n))
+    assert total_v == 94722
+
+
+def test_attention_rejects_unknown_width():
+    with pytest.raises(ValueError):
+        orc.spectral_kernel_size(48)
+    with pytest.raises(ValueError):
+        orc.spatial_kernel_size(48)
