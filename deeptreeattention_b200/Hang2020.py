@@ -1,0 +1,344 @@
+"""Drop-in namespace for the reference's ``src/models/Hang2020.py`` backed by libdta_b200.so.
+
+Same module-level names, constructor signatures, ``forward`` signatures, ``state_dict()``
+keys/shapes/dtypes and train()/eval() semantics as the reference
+(/root/reference/src/models/Hang2020.py:7-278), so an instance can be handed
+to ``TreeModel(model=...)`` (src/main.py:33,50,77) unchanged.  The torch.nn layers below are
+only *parameter containers* (they give the reference's default initialisation and key names);
+the arithmetic of a network forward/backward is one call each into the CUDA library.
+
+No CPU path exists here: a CPU tensor, a missing library or a non-sm_100 device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List
+
+import torch
+from torch import nn
+from torch.nn import Module
+
+from . import _capi
+
+_KIND_PREFIXES = {
+    _capi.NET_HANG2020: ("spectral_network.", "spatial_network."),
+    _capi.NET_SPECTRAL: ("",),
+    _capi.NET_SPATIAL: ("",),
+    _capi.NET_VANILLA: ("",),
+}
+_CONV_FIELDS = {
+    "conv_layer.weight": "conv_w", "conv_layer.bias": "conv_b", "bn1.weight": "bn_w", "bn1.bias": "bn_b",
+    "bn1.running_mean": "bn_rm", "bn1.running_var": "bn_rv", "bn1.num_batches_tracked": "bn_nbt",
+}
+_ATTN_FIELDS = {
+    "channel_pool.weight": "pool_w", "channel_pool.bias": "pool_b",
+    "attention_conv1.weight": "w0", "attention_conv1.bias": "b0",
+    "attention_conv2.weight": "w1", "attention_conv2.bias": "b1",
+}
+
+
+def _fill_tensors(kind: int, ptr_of: Dict[str, int]) -> _capi.Tensors:
+    """Build the C parameter (or gradient) table from {state_dict key: device pointer}."""
+    t = _capi.Tensors()
+    t.alpha = ptr_of.get("alpha", None)
+    for g, prefix in enumerate(_KIND_PREFIXES[kind]):
+        br = t.branch[g]
+        for k in (1, 2, 3):
+            for key, field in _CONV_FIELDS.items():
+                setattr(br.conv[k - 1], field, ptr_of.get(f"{prefix}conv{k}.{key}", None))
+            for key, field in _ATTN_FIELDS.items():
+                setattr(br.attn[k - 1], field, ptr_of.get(f"{prefix}attention_{k}.{key}", None))
+            br.fc_w[k - 1] = ptr_of.get(f"{prefix}classifier{k}.fc1.weight", None)
+            br.fc_b[k - 1] = ptr_of.get(f"{prefix}classifier{k}.fc1.bias", None)
+        if kind == _capi.NET_VANILLA:
+            br.fc_w[2] = ptr_of.get("fc1.weight", None)
+            br.fc_b[2] = ptr_of.get("fc1.bias", None)
+    return t
+
+
+def _head_of_param(kind: int, name: str):
+    """Index of the head whose upstream gradient alone reaches this parameter (classifier
+    weights), else None."""
+    if kind == _capi.NET_VANILLA:
+        return None
+    for g, prefix in enumerate(_KIND_PREFIXES[kind]):
+        for k in (1, 2, 3):
+            if name.startswith(f"{prefix}classifier{k}."):
+                return g * 3 + (k - 1)
+    return None
+
+
+class _NetSpec:
+    """Static description handed to the autograd function."""
+
+    def __init__(self, kind, bands, classes):
+        self.kind, self.bands, self.classes = kind, bands, classes
+        self.n_heads = {_capi.NET_HANG2020: 6, _capi.NET_SPECTRAL: 3, _capi.NET_SPATIAL: 3, _capi.NET_VANILLA: 1}[kind]
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _FusedNetFunction(torch.autograd.Function):
+    """One dta_forward / dta_backward pair (include/dta_b200.h)."""
+
+    @staticmethod
+    def forward(ctx, x, spec: _NetSpec, training: bool, names: List[str], buffers: Dict[str, torch.Tensor], *params):
+        dev = x.device
+        lib = _capi.lib()
+        handle = _capi.context(dev.index if dev.index is not None else torch.cuda.current_device())
+        B = x.shape[0]
+        shape = _capi.Shape(spec.kind, B, spec.bands, spec.classes, int(training))
+        sizes = _capi.query_sizes(spec.kind, B, spec.bands, spec.classes, training)
+        ptr_of = {n: p.data_ptr() for n, p in zip(names, params)}
+        ptr_of.update({n: b.data_ptr() for n, b in buffers.items()})
+        table = _fill_tensors(spec.kind, ptr_of)
+        with torch.cuda.device(dev):
+            scores = [torch.empty((B, spec.classes), dtype=torch.float32, device=dev) for _ in range(spec.n_heads)]
+            joint = torch.empty((B, spec.classes), dtype=torch.float32, device=dev) if spec.kind == _capi.NET_HANG2020 else None
+            saved = torch.empty(sizes.saved_bytes, dtype=torch.uint8, device=dev)
+            work = torch.empty(max(sizes.workspace_fwd, 256), dtype=torch.uint8, device=dev)
+            score_ptrs = (C.c_void_p * 6)(*[s.data_ptr() for s in scores] + [None] * (6 - spec.n_heads))
+            rc = lib.dta_forward(handle, C.byref(shape), x.data_ptr(), C.byref(table), C.byref(score_ptrs),
+                                 joint.data_ptr() if joint is not None else None, saved.data_ptr(), work.data_ptr(),
+                                 _stream_ptr(dev))
+        _capi.check(handle, rc, "dta_forward")
+        ctx.spec, ctx.training, ctx.names, ctx.buffers = spec, training, names, buffers
+        ctx.save_for_backward(x, saved, *params)
+        ctx.set_materialize_grads(False)
+        outs = tuple(scores) + ((joint,) if joint is not None else ())
+        return outs
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        spec = ctx.spec
+        x, saved, *params = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("deeptreeattention_b200: gradient w.r.t. the crops is not built; "
+                                      "the reference feeds requires_grad=False images (src/main.py:75-77)")
+        dev = x.device
+        lib = _capi.lib()
+        handle = _capi.context(dev.index if dev.index is not None else torch.cuda.current_device())
+        B = x.shape[0]
+        shape = _capi.Shape(spec.kind, B, spec.bands, spec.classes, int(ctx.training))
+        sizes = _capi.query_sizes(spec.kind, B, spec.bands, spec.classes, ctx.training)
+        dheads = [g.contiguous().float() if g is not None else None for g in gouts[:spec.n_heads]]
+        djoint = gouts[spec.n_heads] if spec.kind == _capi.NET_HANG2020 else None
+        if djoint is not None:
+            djoint = djoint.contiguous().float()
+        ptr_of = {n: p.data_ptr() for n, p in zip(ctx.names, params)}
+        table = _fill_tensors(spec.kind, ptr_of)
+        with torch.cuda.device(dev):
+            # every float gradient lives in ONE flat buffer (a single all-reduce covers it)
+            numels = [p.numel() if p.dtype == torch.float32 else 0 for p in params]
+            flat = torch.zeros(sum(numels), dtype=torch.float32, device=dev)
+            galpha = torch.zeros((), dtype=torch.float64, device=dev)
+            grads, off = [], 0
+            for p, n in zip(params, numels):
+                if p.dtype == torch.float32:
+                    grads.append(flat[off:off + n].view(p.shape))
+                    off += n
+                else:
+                    grads.append(galpha)
+            gtable = _fill_tensors(spec.kind, {n: g.data_ptr() for n, g in zip(ctx.names, grads)})
+            work = torch.empty(max(sizes.workspace_bwd, 256), dtype=torch.uint8, device=dev)
+            dptrs = (C.c_void_p * 6)(*[(d.data_ptr() if d is not None else None) for d in dheads] + [None] * (6 - spec.n_heads))
+            rc = lib.dta_backward(handle, C.byref(shape), x.data_ptr(), C.byref(table), saved.data_ptr(), C.byref(dptrs),
+                                  djoint.data_ptr() if djoint is not None else None, C.byref(gtable), None,
+                                  work.data_ptr(), _stream_ptr(dev))
+        _capi.check(handle, rc, "dta_backward")
+        out = []
+        for name, g, need in zip(ctx.names, grads, ctx.needs_input_grad[5:]):
+            if not need:
+                out.append(None)
+                continue
+            h = _head_of_param(spec.kind, name)
+            if h is not None:
+                reached = dheads[h] is not None or (djoint is not None and h in (2, 5))
+                out.append(g if reached else None)     # reference: grad None for unused heads
+            elif name == "alpha":
+                out.append(g if djoint is not None else None)
+            else:
+                out.append(g)
+        return (None, None, None, None, None) + tuple(out)
+
+
+class _FusedNet(Module):
+    """Mixin: runs the whole network through the library."""
+    _net_kind = None
+
+    def _fused(self, x: torch.Tensor):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("expected a tensor of crops (B, bands, 11, 11)")
+        if not x.is_cuda:
+            raise RuntimeError("deeptreeattention_b200 has no CPU path: move the model and the crops to a CUDA (sm_100) device")
+        if x.dtype != torch.float32:
+            raise TypeError(f"crops must be float32, got {x.dtype}")
+        if x.dim() != 4 or x.shape[1] != self._bands or x.shape[2] != 11 or x.shape[3] != 11:
+            raise ValueError(f"expected crops of shape (B, {self._bands}, 11, 11), got {tuple(x.shape)}")
+        x = x.contiguous()
+        sd = self.state_dict(keep_vars=True)
+        names, params, buffers = [], [], {}
+        for k, v in sd.items():
+            if isinstance(v, nn.Parameter):
+                names.append(k)
+                params.append(v)
+            else:
+                buffers[k] = v
+        for p in params:
+            if p.device != x.device:
+                raise RuntimeError(f"parameter on {p.device} but crops on {x.device}")
+        spec = _NetSpec(self._net_kind, self._bands, self._classes)
+        return _FusedNetFunction.apply(x, spec, self.training, names, buffers, *params)
+
+
+# ------------------------------------------------------------------- reference API surface
+def global_spectral_pool(x):
+    """Mean over H, W keeping a trailing singleton (reference Hang2020.py:7-12).  Host-side
+    helper only; inside the networks this is fused into the attention kernels."""
+    return torch.mean(x, dim=(2, 3)).unsqueeze(-1)
+
+
+def _block_only(name):
+    raise NotImplementedError(
+        f"{name}: stand-alone block forward is not built yet; use the network modules "
+        "(Hang2020 / spectral_network / spatial_network / vanilla_CNN), which run fused")
+
+
+class conv_module(Module):
+    """Conv2d 3x3 'same' + BatchNorm2d + ReLU (+ MaxPool2d) block (reference :14-31)."""
+
+    def __init__(self, in_channels, filters, maxpool_kernel=None):
+        super().__init__()
+        self.conv_layer = nn.Conv2d(in_channels, out_channels=filters, kernel_size=(3, 3), padding="same")
+        self.bn1 = nn.BatchNorm2d(filters)
+        self.maxpool_kernal = maxpool_kernel
+        if maxpool_kernel:
+            self.max_pool = nn.MaxPool2d(maxpool_kernel)
+
+    def forward(self, x, pool=False):
+        _block_only("conv_module")
+
+
+class Classifier(Module):
+    """Linear head (reference :55-66)."""
+
+    def __init__(self, in_features, classes):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features=in_features, out_features=classes)
+
+    def forward(self, features):
+        _block_only("Classifier")
+
+
+class spatial_attention(Module):
+    """Pixel gate: 1x1 channel pool, two k x k stencils, class max-pool (reference :68-124)."""
+
+    def __init__(self, filters):
+        super().__init__()
+        sizes = {32: (7, 4), 64: (5, 2), 128: (3, 1)}
+        if filters not in sizes:
+            raise ValueError("Unknown incoming kernel size {} for attention layers".format(filters))
+        kernel_size, pool = sizes[filters]
+        self.channel_pool = nn.Conv2d(in_channels=filters, out_channels=1, kernel_size=1)
+        self.attention_conv1 = nn.Conv2d(1, 1, kernel_size=kernel_size, padding="same")
+        self.attention_conv2 = nn.Conv2d(1, 1, kernel_size=kernel_size, padding="same")
+        self.class_pool = nn.MaxPool2d((pool, pool))
+
+    def forward(self, x):
+        _block_only("spatial_attention")
+
+
+class spectral_attention(Module):
+    """Channel gate: squeeze, two Conv1d on a length-1 sequence, sigmoid (reference :126-168)."""
+
+    def __init__(self, filters):
+        super().__init__()
+        sizes = {32: 3, 64: 5, 128: 7}
+        if filters not in sizes:
+            raise ValueError("Unknown incoming kernel size {} for attention layers".format(filters))
+        kernel_size = sizes[filters]
+        self.attention_conv1 = nn.Conv1d(filters, filters, kernel_size=kernel_size, padding="same")
+        self.attention_conv2 = nn.Conv1d(filters, filters, kernel_size=kernel_size, padding="same")
+
+    def forward(self, x):
+        _block_only("spectral_attention")
+
+
+class _Branch(_FusedNet):
+    _attention = None
+    _features = None
+
+    def __init__(self, bands, classes):
+        super().__init__()
+        self._bands, self._classes = int(bands), int(classes)
+        cin = bands
+        for k, (c, f) in enumerate(zip((32, 64, 128), self._features), start=1):
+            setattr(self, f"conv{k}", conv_module(in_channels=cin, filters=c, maxpool_kernel=(2, 2) if k > 1 else None))
+            setattr(self, f"attention_{k}", self._attention(filters=c))
+            setattr(self, f"classifier{k}", Classifier(classes=classes, in_features=f))
+            cin = c
+
+    def forward(self, x):
+        """Returns [scores1, scores2, scores3] like the reference (:190-204 / :226-240)."""
+        return list(self._fused(x))
+
+
+class spatial_network(_Branch):
+    """Reference :170-204."""
+    _net_kind = _capi.NET_SPATIAL
+    _attention = spatial_attention
+    _features = (128, 256, 512)
+
+
+class spectral_network(_Branch):
+    """Reference :206-240."""
+    _net_kind = _capi.NET_SPECTRAL
+    _attention = spectral_attention
+    _features = (32, 64, 128)
+
+
+class vanilla_CNN(_FusedNet):
+    """Baseline without attention (reference :33-53)."""
+    _net_kind = _capi.NET_VANILLA
+
+    def __init__(self, bands, classes):
+        super().__init__()
+        self._bands, self._classes = int(bands), int(classes)
+        self.conv1 = conv_module(in_channels=bands, filters=32)
+        self.conv2 = conv_module(in_channels=32, filters=64, maxpool_kernel=(2, 2))
+        self.conv3 = conv_module(in_channels=64, filters=128, maxpool_kernel=(2, 2))
+        self.fc1 = nn.Linear(in_features=512, out_features=classes)
+
+    def forward(self, x):
+        return self._fused(x)[0]
+
+
+class Hang2020(_FusedNet):
+    """Both branches on the same crops, alpha-blended last heads (reference :242-263)."""
+    _net_kind = _capi.NET_HANG2020
+
+    def __init__(self, bands, classes):
+        super().__init__()
+        self._bands, self._classes = int(bands), int(classes)
+        self.spectral_network = spectral_network(bands, classes)
+        self.spatial_network = spatial_network(bands, classes)
+        self.alpha = nn.Parameter(torch.tensor(0.5, dtype=float), requires_grad=True)
+
+    def forward(self, x):
+        outs = self._fused(x)
+        self.head_scores = list(outs[:6])        # spectral 1-3, spatial 1-3 (extra over the reference)
+        self.weighted_average = torch.sigmoid(self.alpha.detach())
+        return outs[6]
+
+
+def load_from_backbone(state_dict, classes, bands):
+    """Fresh spectral_network with every non-classifier tensor taken from a saved
+    spectral_network state_dict file (reference :266-278)."""
+    saved = torch.load(state_dict, map_location="cpu")
+    model = spectral_network(classes=classes, bands=bands)
+    merged = model.state_dict()
+    merged.update({k: v for k, v in saved.items() if "classifier" not in k})
+    model.load_state_dict(merged)
+    return model

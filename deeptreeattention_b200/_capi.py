@@ -1,0 +1,179 @@
+"""ctypes binding of libdta_b200.so (include/dta_b200.h) and the in-tree nvcc build.
+
+There is deliberately no CPU fallback: if the library cannot be built/loaded or there is
+no sm_100 device, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_PATH = os.path.join(HERE, "libdta_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+DTA_OK = 0
+NET_HANG2020, NET_SPECTRAL, NET_SPATIAL, NET_VANILLA = 0, 1, 2, 3
+
+
+class Shape(C.Structure):
+    _fields_ = [("net_kind", C.c_int32), ("batch", C.c_int32), ("bands", C.c_int32),
+                ("classes", C.c_int32), ("training", C.c_int32)]
+
+
+class ConvBlock(C.Structure):
+    _fields_ = [("conv_w", C.c_void_p), ("conv_b", C.c_void_p), ("bn_w", C.c_void_p), ("bn_b", C.c_void_p),
+                ("bn_rm", C.c_void_p), ("bn_rv", C.c_void_p), ("bn_nbt", C.c_void_p)]
+
+
+class Attention(C.Structure):
+    _fields_ = [("pool_w", C.c_void_p), ("pool_b", C.c_void_p), ("w0", C.c_void_p), ("b0", C.c_void_p),
+                ("w1", C.c_void_p), ("b1", C.c_void_p)]
+
+
+class Branch(C.Structure):
+    _fields_ = [("conv", ConvBlock * 3), ("attn", Attention * 3), ("fc_w", C.c_void_p * 3), ("fc_b", C.c_void_p * 3)]
+
+
+class Tensors(C.Structure):
+    _fields_ = [("alpha", C.c_void_p), ("branch", Branch * 2)]
+
+
+class Sizes(C.Structure):
+    _fields_ = [("saved_bytes", C.c_size_t), ("workspace_fwd", C.c_size_t), ("workspace_bwd", C.c_size_t),
+                ("n_heads", C.c_int32)]
+
+
+EXPORTS = ["dta_abi_version", "dta_create", "dta_destroy", "dta_last_error", "dta_set_option", "dta_get_option",
+           "dta_query_sizes", "dta_forward", "dta_backward"]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + [os.path.join(os.path.dirname(HERE), "include", "dta_b200.h")]
+    return any(os.path.getmtime(s) > t for s in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libdta_b200.so next to this file (in-tree, so the
+    binary travels with the repo snapshot)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libdta_b200.so (no CPU fallback exists)")
+    cu = [s for s in sources() if s.endswith(".cu")]
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc] + NVCC_FLAGS + cu + ["-o", tmp]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load (building first when sources are newer and nvcc exists) the C-ABI library."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if needs_build():
+            if os.path.exists(LIB_PATH) and not (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+                pass  # prebuilt binary on a box without nvcc: use it
+            else:
+                build()
+        L = C.CDLL(LIB_PATH)
+        L.dta_abi_version.restype = C.c_int
+        L.dta_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.dta_create.restype = C.c_int
+        L.dta_destroy.argtypes = [C.c_void_p]
+        L.dta_destroy.restype = None
+        L.dta_last_error.argtypes = [C.c_void_p]
+        L.dta_last_error.restype = C.c_char_p
+        L.dta_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        L.dta_set_option.restype = C.c_int
+        L.dta_get_option.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
+        L.dta_get_option.restype = C.c_int
+        L.dta_query_sizes.argtypes = [C.POINTER(Shape), C.POINTER(Sizes)]
+        L.dta_query_sizes.restype = C.c_int
+        L.dta_forward.argtypes = [C.c_void_p, C.POINTER(Shape), C.c_void_p, C.POINTER(Tensors),
+                                  C.POINTER(C.c_void_p * 6), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.dta_forward.restype = C.c_int
+        L.dta_backward.argtypes = [C.c_void_p, C.POINTER(Shape), C.c_void_p, C.POINTER(Tensors), C.c_void_p,
+                                   C.POINTER(C.c_void_p * 6), C.c_void_p, C.POINTER(Tensors), C.c_void_p,
+                                   C.c_void_p, C.c_void_p]
+        L.dta_backward.restype = C.c_int
+        _lib = L
+        return L
+
+
+class DtaError(RuntimeError):
+    pass
+
+
+_ctxs = {}
+
+
+def context(device_index: int):
+    """One dta_ctx per CUDA device per process."""
+    L = lib()
+    h = _ctxs.get(device_index)
+    if h is None:
+        out = C.c_void_p()
+        rc = L.dta_create(C.byref(out), device_index)
+        if rc != DTA_OK:
+            raise DtaError(f"dta_create failed ({rc}): {L.dta_last_error(None).decode()}")
+        h = out
+        _ctxs[device_index] = h
+    return h
+
+
+def check(ctx, rc: int, what: str):
+    if rc != DTA_OK:
+        msg = lib().dta_last_error(ctx).decode()
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise DtaError(f"{what} failed ({rc}): {msg}")
+
+
+def query_sizes(net_kind: int, batch: int, bands: int, classes: int, training: bool) -> Sizes:
+    s = Shape(net_kind, batch, bands, classes, int(training))
+    out = Sizes()
+    rc = lib().dta_query_sizes(C.byref(s), C.byref(out))
+    if rc != DTA_OK:
+        raise ValueError(f"dta_query_sizes rejected shape (kind={net_kind}, batch={batch}, bands={bands}, classes={classes})")
+    return out
+
+
+def set_option(device_index: int, key: str, value: int):
+    ctx = context(device_index)
+    check(ctx, lib().dta_set_option(ctx, key.encode(), int(value)), f"dta_set_option({key})")
+
+
+def get_option(device_index: int, key: str) -> int:
+    ctx = context(device_index)
+    v = C.c_int64()
+    rc = lib().dta_get_option(ctx, key.encode(), C.byref(v))
+    if rc != DTA_OK:
+        raise ValueError(f"unknown option {key}")
+    return v.value

@@ -1,0 +1,673 @@
+// C ABI of libdta_b200.so: context, buffer-size arithmetic and the forward / backward
+// launch sequences (see include/dta_b200.h for the contract and DESIGN.md for the plan).
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "dta_attention.cuh"
+#include "dta_common.cuh"
+#include "dta_conv_simt.cuh"
+#include "dta_misc.cuh"
+
+using namespace dta;
+
+struct dta_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int conv_impl = 0;
+  long long launches = 0;
+  std::string err;
+};
+
+static std::string g_create_error;
+
+namespace {
+
+constexpr int kC[3] = {32, 64, 128};
+constexpr int kHWpre[3] = {121, 121, 25};   // conv output plane per block
+constexpr int kHWpost[3] = {121, 25, 4};    // after the block's max-pool
+constexpr int kAttRow[3] = {121, 64, 128};  // AttnCfg::ROW
+constexpr int kFeatLd[3] = {128, 256, 512};
+constexpr int kProwLd[3] = {AttnBwdRow<32, 11, false>::LD, AttnBwdRow<64, 11, true>::LD, AttnBwdRow<128, 5, true>::LD};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct NetDesc {
+  int nb;
+  int btype[2];
+  int n_heads;
+};
+
+bool describe(int kind, NetDesc* d) {
+  switch (kind) {
+    case DTA_NET_HANG2020: *d = {2, {BR_SPECTRAL, BR_SPATIAL}, 6}; return true;
+    case DTA_NET_SPECTRAL: *d = {1, {BR_SPECTRAL, BR_NONE}, 3}; return true;
+    case DTA_NET_SPATIAL: *d = {1, {BR_SPATIAL, BR_NONE}, 3}; return true;
+    case DTA_NET_VANILLA: *d = {1, {BR_NONE, BR_NONE}, 1}; return true;
+    default: return false;
+  }
+}
+
+// Carves float regions (256-byte aligned) out of one caller-owned buffer.
+struct Carver {
+  size_t off = 0;
+  char* base;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  float* take(size_t nfloats) {
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += align_up(nfloats * sizeof(float), 256);
+    return p;
+  }
+};
+
+struct SavedLayout {
+  float* z[3];
+  float* bn_mean[3]; float* bn_istd[3]; float* bn_scale[3]; float* bn_shift[3];
+  float* att[3];
+  float* feat[3];
+  float* s3[2];
+  float* wp[3];
+  float* spec_pack[2][3][4];  // [branch][block][w0d, w0t, w1d, w1t]
+  size_t bytes;
+};
+
+SavedLayout layout_saved(const dta_shape& s, const NetDesc& d, void* base) {
+  SavedLayout L{};
+  Carver c(base);
+  const size_t B = s.batch;
+  for (int k = 0; k < 3; ++k) L.z[k] = c.take(B * d.nb * kC[k] * kHWpre[k]);
+  for (int k = 0; k < 3; ++k) {
+    L.bn_mean[k] = c.take(d.nb * kC[k]); L.bn_istd[k] = c.take(d.nb * kC[k]);
+    L.bn_scale[k] = c.take(d.nb * kC[k]); L.bn_shift[k] = c.take(d.nb * kC[k]);
+  }
+  for (int k = 0; k < 3; ++k) L.att[k] = c.take(B * d.nb * 3 * kAttRow[k]);
+  for (int k = 0; k < 3; ++k) L.feat[k] = c.take(B * d.nb * kFeatLd[k]);
+  for (int g = 0; g < 2; ++g) L.s3[g] = c.take(B * s.classes);
+  L.wp[0] = c.take((size_t)s.bands * 9 * d.nb * 32);
+  L.wp[1] = c.take((size_t)d.nb * 32 * 9 * 64);
+  L.wp[2] = c.take((size_t)d.nb * 64 * 9 * 128);
+  for (int g = 0; g < 2; ++g)
+    for (int k = 0; k < 3; ++k)
+      for (int q = 0; q < 4; ++q) L.spec_pack[g][k][q] = c.take((size_t)kC[k] * kC[k]);
+  L.bytes = c.off;
+  return L;
+}
+
+struct FwdWork {
+  float* stats;
+  size_t bytes;
+};
+FwdWork layout_fwd(const dta_shape& s, const NetDesc& d, void* base) {
+  FwdWork W{};
+  Carver c(base);
+  W.stats = c.take((size_t)s.batch * d.nb * 128 * 2);
+  W.bytes = c.off;
+  return W;
+}
+
+// wgrad split-K factors (batch slices per weight-gradient CTA column)
+struct Splits { int n[3]; int per[3]; };
+Splits wgrad_splits(int B) {
+  Splits sp;
+  const int want[3] = {24, 128, 64};
+  for (int k = 0; k < 3; ++k) {
+    int n = want[k] < B ? want[k] : B;
+    int per = (B + n - 1) / n;
+    n = (B + per - 1) / per;
+    sp.n[k] = n; sp.per[k] = per;
+  }
+  return sp;
+}
+
+struct BwdWork {
+  float* dS[6];
+  float* da[3];
+  float* dout[2];   // gradient wrt gated output of block 1, 2
+  float* bnrows;
+  float* k0[3]; float* k1[3]; float* k2[3];
+  float* prow;
+  float* wpart;
+  float* wd[3];
+  size_t bytes;
+};
+BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
+  BwdWork W{};
+  Carver c(base);
+  const size_t B = s.batch;
+  for (int h = 0; h < 6; ++h) W.dS[h] = c.take(B * s.classes);
+  for (int k = 0; k < 3; ++k) W.da[k] = c.take(B * d.nb * kC[k] * kHWpre[k]);
+  W.dout[0] = c.take(B * d.nb * 32 * 121);
+  W.dout[1] = c.take(B * d.nb * 64 * 25);
+  W.bnrows = c.take(B * d.nb * 256);
+  for (int k = 0; k < 3; ++k) { W.k0[k] = c.take(d.nb * kC[k]); W.k1[k] = c.take(d.nb * kC[k]); W.k2[k] = c.take(d.nb * kC[k]); }
+  W.prow = c.take(B * d.nb * 256);
+  const Splits sp = wgrad_splits(s.batch);
+  size_t wp = (size_t)sp.n[0] * d.nb * 32 * s.bands * 9;
+  const size_t wp2 = (size_t)sp.n[1] * d.nb * 64 * 32 * 9, wp3 = (size_t)sp.n[2] * d.nb * 128 * 64 * 9;
+  if (wp2 > wp) wp = wp2;
+  if (wp3 > wp) wp = wp3;
+  W.wpart = c.take(wp);
+  W.wd[0] = c.take((size_t)d.nb * 32 * 9 * s.bands);
+  W.wd[1] = c.take((size_t)d.nb * 64 * 9 * 32);
+  W.wd[2] = c.take((size_t)d.nb * 128 * 9 * 64);
+  W.bytes = c.off;
+  return W;
+}
+
+int fail(dta_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define DTA_CHECK_LAUNCH(ctx, what)                                                        \
+  do {                                                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess)                                                                \
+      return fail(ctx, DTA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e__));  \
+    (ctx)->launches++;                                                                     \
+  } while (0)
+
+int check_shape(dta_ctx* ctx, const dta_shape* s, NetDesc* d) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  if (!s) return fail(ctx, DTA_ERR_INVALID_ARG, "shape is NULL");
+  if (!describe(s->net_kind, d)) return fail(ctx, DTA_ERR_INVALID_ARG, "unknown net_kind");
+  if (s->batch <= 0 || s->bands <= 0 || s->classes <= 0) return fail(ctx, DTA_ERR_INVALID_ARG, "batch, bands and classes must be positive");
+  if (s->classes > 4096) return fail(ctx, DTA_ERR_UNSUPPORTED, "classes > 4096 not supported");
+  return DTA_OK;
+}
+
+template <typename K>
+cudaError_t allow_smem(K kernel, size_t bytes) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// ---- convolution launchers (conv_impl 0) ----------------------------------------------
+template <int S, int NCROP, int TP, int TC, int COUT, int CK>
+cudaError_t launch_fprop(const ConvSrc& src, const float* wp, Ptr2 bias, int bias_split, float* out, int out_ctot,
+                         float* stats, int B, int G, cudaStream_t st, int* nblk) {
+  using Cfg = FpropCfg<S, NCROP, TP, TC, COUT, CK>;
+  auto kern = conv3x3_fprop_simt<S, NCROP, TP, TC, COUT, CK>;
+  cudaError_t e = allow_smem(kern, Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  dim3 grid((B + NCROP - 1) / NCROP, G);
+  if (nblk) *nblk = grid.x;
+  kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>(src, wp, bias, bias_split, out, out_ctot, stats, B);
+  return cudaGetLastError();
+}
+
+template <int S, int CIK, int COUT, int TCO>
+cudaError_t launch_wgrad(const ConvSrc& in, const ConvSrc& dz, float* part, int B, int nsplit, int per, int G,
+                         cudaStream_t st) {
+  using Cfg = WgradCfg<S, CIK, COUT, TCO>;
+  auto kern = conv3x3_wgrad_simt<S, CIK, COUT, TCO>;
+  cudaError_t e = allow_smem(kern, Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  dim3 grid((in.cin + CIK - 1) / CIK, nsplit, G);
+  kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>(in, dz, part, B, per);
+  return cudaGetLastError();
+}
+
+ConvSrc src_raw(const float* x, int cin, int hw) {
+  ConvSrc s{};
+  s.mode = SRC_RAW; s.cin = cin; s.ctot = cin; s.src_hw = hw; s.a = x;
+  return s;
+}
+ConvSrc src_act(const float* z, int cin, int nb, int src_hw, int pool, const float* scale, const float* shift,
+                const float* gate, int gate_ld, int gate_off, const int* btype) {
+  ConvSrc s{};
+  s.mode = SRC_ACT; s.cin = cin; s.ctot = nb * cin; s.src_hw = src_hw; s.pool = pool; s.a = z;
+  s.k0 = scale; s.k1 = shift; s.gate = gate; s.gate_ld = gate_ld; s.gate_off = gate_off;
+  s.gate_mode[0] = btype[0]; s.gate_mode[1] = btype[1];
+  return s;
+}
+ConvSrc src_dz(const float* da, const float* z, int cin, int ctot, int hw, const float* k0, const float* k1,
+               const float* k2) {
+  ConvSrc s{};
+  s.mode = SRC_DZ; s.cin = cin; s.ctot = ctot; s.src_hw = hw; s.a = da; s.b = z; s.k0 = k0; s.k1 = k1; s.k2 = k2;
+  return s;
+}
+
+AttnParams attn_params(const dta_tensors* p, const SavedLayout& L, const NetDesc& d, int k, bool vanilla_head) {
+  AttnParams a{};
+  for (int g = 0; g < 2; ++g) {
+    a.btype[g] = d.btype[g];
+    if (g >= d.nb) continue;
+    const dta_branch& br = p->branch[g];
+    if (d.btype[g] == BR_SPECTRAL) {
+      a.w0d[g] = L.spec_pack[g][k][0]; a.w0t[g] = L.spec_pack[g][k][1];
+      a.w1d[g] = L.spec_pack[g][k][2]; a.w1t[g] = L.spec_pack[g][k][3];
+      a.b0[g] = br.attn[k].b0; a.b1[g] = br.attn[k].b1;
+    } else if (d.btype[g] == BR_SPATIAL) {
+      a.st0[g] = br.attn[k].w0; a.st1[g] = br.attn[k].w1;
+      a.b0[g] = br.attn[k].b0; a.b1[g] = br.attn[k].b1;
+      a.pool_w[g] = br.attn[k].pool_w; a.pool_b[g] = br.attn[k].pool_b;
+    }
+    if (d.btype[g] != BR_NONE || vanilla_head) { a.fc_w[g] = br.fc_w[k]; a.fc_b[g] = br.fc_b[k]; }
+  }
+  return a;
+}
+
+BnParams bn_params(const dta_tensors* p, const NetDesc& d, int k) {
+  BnParams b{};
+  for (int g = 0; g < d.nb; ++g) {
+    const dta_conv_block& cb = p->branch[g].conv[k];
+    b.gamma[g] = cb.bn_w; b.beta[g] = cb.bn_b; b.rm[g] = cb.bn_rm; b.rv[g] = cb.bn_rv;
+    b.nbt[g] = reinterpret_cast<long long*>(cb.bn_nbt);
+  }
+  b.c_per_branch = kC[k];
+  return b;
+}
+
+int validate_params(dta_ctx* ctx, const dta_tensors* p, const NetDesc& d, int kind, bool need_running) {
+  if (!p) return fail(ctx, DTA_ERR_INVALID_ARG, "params is NULL");
+  if (kind == DTA_NET_HANG2020 && !p->alpha) return fail(ctx, DTA_ERR_INVALID_ARG, "alpha is NULL");
+  for (int g = 0; g < d.nb; ++g) {
+    const dta_branch& br = p->branch[g];
+    for (int k = 0; k < 3; ++k) {
+      const dta_conv_block& cb = br.conv[k];
+      if (!cb.conv_w || !cb.conv_b || !cb.bn_w || !cb.bn_b) return fail(ctx, DTA_ERR_INVALID_ARG, "conv block parameter is NULL");
+      if (need_running && (!cb.bn_rm || !cb.bn_rv)) return fail(ctx, DTA_ERR_INVALID_ARG, "BatchNorm running statistics are NULL");
+      const dta_attention& at = br.attn[k];
+      if (d.btype[g] != BR_NONE && (!at.w0 || !at.b0 || !at.w1 || !at.b1)) return fail(ctx, DTA_ERR_INVALID_ARG, "attention parameter is NULL");
+      if (d.btype[g] == BR_SPATIAL && (!at.pool_w || !at.pool_b)) return fail(ctx, DTA_ERR_INVALID_ARG, "channel_pool parameter is NULL");
+      if ((d.btype[g] != BR_NONE || k == 2) && (!br.fc_w[k] || !br.fc_b[k])) return fail(ctx, DTA_ERR_INVALID_ARG, "classifier parameter is NULL");
+    }
+  }
+  return DTA_OK;
+}
+
+}  // namespace
+
+// =======================================================================================
+extern "C" {
+
+int dta_abi_version(void) { return DTA_ABI_VERSION; }
+
+int dta_create(dta_ctx** out, int device) {
+  if (!out) return DTA_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+    cudaGetLastError();
+    return DTA_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= n) { g_create_error = "device index out of range"; return DTA_ERR_INVALID_ARG; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return DTA_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = "device is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this library is built for sm_100a only";
+    return DTA_ERR_NO_DEVICE;
+  }
+  dta_ctx* c = new dta_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return DTA_OK;
+}
+
+void dta_destroy(dta_ctx* ctx) { delete ctx; }
+
+const char* dta_last_error(const dta_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dta_set_option(dta_ctx* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return DTA_ERR_INVALID_ARG;
+  if (!strcmp(key, "conv_impl")) {
+    if (value != 0) return fail(ctx, DTA_ERR_UNSUPPORTED, "conv_impl: only 0 (fp32 direct) is built in this version");
+    ctx->conv_impl = (int)value;
+    return DTA_OK;
+  }
+  return fail(ctx, DTA_ERR_INVALID_ARG, std::string("unknown option ") + key);
+}
+
+int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value) {
+  if (!ctx || !key || !value) return DTA_ERR_INVALID_ARG;
+  if (!strcmp(key, "conv_impl")) { *value = ctx->conv_impl; return DTA_OK; }
+  if (!strcmp(key, "launches")) { *value = ctx->launches; return DTA_OK; }
+  if (!strcmp(key, "sm_count")) { *value = ctx->sm_count; return DTA_OK; }
+  return DTA_ERR_INVALID_ARG;
+}
+
+int dta_query_sizes(const dta_shape* shape, dta_sizes* out) {
+  NetDesc d;
+  if (!shape || !out || !describe(shape->net_kind, &d)) return DTA_ERR_INVALID_ARG;
+  if (shape->batch <= 0 || shape->bands <= 0 || shape->classes <= 0) return DTA_ERR_INVALID_ARG;
+  out->saved_bytes = layout_saved(*shape, d, nullptr).bytes;
+  out->workspace_fwd = layout_fwd(*shape, d, nullptr).bytes;
+  out->workspace_bwd = layout_bwd(*shape, d, nullptr).bytes;
+  out->n_heads = d.n_heads;
+  return DTA_OK;
+}
+
+int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_tensors* params,
+                float* const scores[6], float* joint, void* saved, void* workspace, void* cuda_stream) {
+  NetDesc d;
+  int rc = check_shape(ctx, shape, &d);
+  if (rc != DTA_OK) return rc;
+  if (!x || !scores || !saved || !workspace) return fail(ctx, DTA_ERR_INVALID_ARG, "x, scores, saved and workspace are required");
+  rc = validate_params(ctx, params, d, shape->net_kind, true);
+  if (rc != DTA_OK) return rc;
+  for (int h = 0; h < d.n_heads; ++h)
+    if (!scores[h]) return fail(ctx, DTA_ERR_INVALID_ARG, "scores[h] is NULL for an existing head");
+  if (shape->net_kind == DTA_NET_HANG2020 && !joint) return fail(ctx, DTA_ERR_INVALID_ARG, "joint is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
+  cudaGetLastError();
+  ctx->launches = 0;
+
+  const int B = shape->batch, nb = d.nb, bands = shape->bands, classes = shape->classes;
+  const bool vanilla = shape->net_kind == DTA_NET_VANILLA;
+  SavedLayout L = layout_saved(*shape, d, saved);
+  FwdWork W = layout_fwd(*shape, d, workspace);
+
+  // 1. pack parameters into kernel-friendly tables (a few MB, once per step)
+  for (int k = 0; k < 3; ++k) {
+    Ptr2 w{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}};
+    const int cin = k == 0 ? bands : kC[k - 1];
+    pack_conv_w_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, kC[k], cin, k == 0 ? 1 : 0, L.wp[k]);
+    DTA_CHECK_LAUNCH(ctx, "pack_conv_w");
+  }
+  for (int g = 0; g < nb; ++g) {
+    if (d.btype[g] != BR_SPECTRAL) continue;
+    for (int k = 0; k < 3; ++k) {
+      const int ks = k == 0 ? 3 : (k == 1 ? 5 : 7);  // Hang2020.py:136-141
+      pack_spectral_kernel<<<(kC[k] * kC[k] + 255) / 256, 256, 0, st>>>(params->branch[g].attn[k].w0, kC[k], ks, L.spec_pack[g][k][0], L.spec_pack[g][k][1]);
+      DTA_CHECK_LAUNCH(ctx, "pack_spectral");
+      pack_spectral_kernel<<<(kC[k] * kC[k] + 255) / 256, 256, 0, st>>>(params->branch[g].attn[k].w1, kC[k], ks, L.spec_pack[g][k][2], L.spec_pack[g][k][3]);
+      DTA_CHECK_LAUNCH(ctx, "pack_spectral");
+    }
+  }
+
+  cudaError_t e;
+  int nblk = 0;
+  // 2. block 1: conv1 over the crops (both branches share the read of x)
+  {
+    ConvSrc src = src_raw(x, bands, kHW);
+    Ptr2 bias{{params->branch[0].conv[0].conv_b, nb > 1 ? params->branch[1].conv[0].conv_b : nullptr}};
+    float* stats = shape->training ? W.stats : nullptr;
+    if (nb == 2) e = launch_fprop<11, 1, 8, 8, 64, 16>(src, L.wp[0], bias, 32, L.z[0], 64, stats, B, 1, st, &nblk);
+    else e = launch_fprop<11, 1, 8, 8, 32, 16>(src, L.wp[0], bias, 32, L.z[0], 32, stats, B, 1, st, &nblk);
+    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv1 fprop: ") + cudaGetErrorString(e));
+    ctx->launches++;
+  }
+  auto bn_finalize = [&](int k, int nblk_k) -> int {
+    const int ctot = nb * kC[k];
+    bn_fwd_finalize_kernel<<<(ctot * 32 + 255) / 256, 256, 0, st>>>(W.stats, nblk_k, ctot, (double)B * kHWpre[k], bn_params(params, d, k),
+                                                                    shape->training, L.bn_mean[k], L.bn_istd[k], L.bn_scale[k], L.bn_shift[k]);
+    DTA_CHECK_LAUNCH(ctx, "bn_fwd_finalize");
+    return DTA_OK;
+  };
+  auto score_ptrs = [&](int k) {
+    MutPtr2 m{{nullptr, nullptr}};
+    if (vanilla) { if (k == 2) m.p[0] = scores[0]; return m; }
+    for (int g = 0; g < nb; ++g) m.p[g] = scores[g * 3 + k];
+    return m;
+  };
+  if ((rc = bn_finalize(0, nblk)) != DTA_OK) return rc;
+  if (!vanilla) {
+    auto kern = attn_fwd_kernel<32, 11, false>;
+    const size_t sm = attn_fwd_smem<32, 11, false>();
+    allow_smem(kern, sm);
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], attn_params(params, L, d, 0, false), classes, L.att[0], L.feat[0], score_ptrs(0));
+    DTA_CHECK_LAUNCH(ctx, "attn_fwd<1>");
+  }
+  // 3. block 2
+  {
+    ConvSrc src = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
+    Ptr2 bias{{params->branch[0].conv[1].conv_b, nb > 1 ? params->branch[1].conv[1].conv_b : nullptr}};
+    e = launch_fprop<11, 1, 8, 8, 64, 16>(src, L.wp[1], bias, 64, L.z[1], nb * 64, shape->training ? W.stats : nullptr, B, nb, st, &nblk);
+    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 fprop: ") + cudaGetErrorString(e));
+    ctx->launches++;
+  }
+  if ((rc = bn_finalize(1, nblk)) != DTA_OK) return rc;
+  if (!vanilla) {
+    auto kern = attn_fwd_kernel<64, 11, true>;
+    const size_t sm = attn_fwd_smem<64, 11, true>();
+    allow_smem(kern, sm);
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], attn_params(params, L, d, 1, false), classes, L.att[1], L.feat[1], score_ptrs(1));
+    DTA_CHECK_LAUNCH(ctx, "attn_fwd<2>");
+  }
+  // 4. block 3
+  {
+    ConvSrc src = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
+    Ptr2 bias{{params->branch[0].conv[2].conv_b, nb > 1 ? params->branch[1].conv[2].conv_b : nullptr}};
+    e = launch_fprop<5, 4, 4, 8, 128, 8>(src, L.wp[2], bias, 128, L.z[2], nb * 128, shape->training ? W.stats : nullptr, B, nb, st, &nblk);
+    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 fprop: ") + cudaGetErrorString(e));
+    ctx->launches++;
+  }
+  if ((rc = bn_finalize(2, nblk)) != DTA_OK) return rc;
+  {
+    auto kern = attn_fwd_kernel<128, 5, true>;
+    const size_t sm = attn_fwd_smem<128, 5, true>();
+    allow_smem(kern, sm);
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], attn_params(params, L, d, 2, vanilla), classes, L.att[2], L.feat[2], score_ptrs(2));
+    DTA_CHECK_LAUNCH(ctx, "attn_fwd<3>");
+  }
+  // 5. alpha blend + copies of the last-head scores for dalpha
+  if (shape->net_kind == DTA_NET_HANG2020) {
+    const size_t n = (size_t)B * classes;
+    joint_fwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(scores[2], scores[5], params->alpha, joint, n);
+    DTA_CHECK_LAUNCH(ctx, "joint_fwd");
+    cudaMemcpyAsync(L.s3[0], scores[2], n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(L.s3[1], scores[5], n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("forward: ") + cudaGetErrorString(e));
+  return DTA_OK;
+}
+
+int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_tensors* params,
+                 const void* saved, const float* const dscores[6], const float* djoint,
+                 const dta_tensors* grads, float* dx, void* workspace, void* cuda_stream) {
+  NetDesc d;
+  int rc = check_shape(ctx, shape, &d);
+  if (rc != DTA_OK) return rc;
+  if (!x || !saved || !workspace || !grads || !dscores) return fail(ctx, DTA_ERR_INVALID_ARG, "x, saved, workspace, dscores and grads are required");
+  rc = validate_params(ctx, params, d, shape->net_kind, false);
+  if (rc != DTA_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
+  cudaGetLastError();
+  ctx->launches = 0;
+
+  const int B = shape->batch, nb = d.nb, bands = shape->bands, classes = shape->classes;
+  const bool vanilla = shape->net_kind == DTA_NET_VANILLA;
+  const bool hang = shape->net_kind == DTA_NET_HANG2020;
+  SavedLayout L = layout_saved(*shape, d, const_cast<void*>(saved));
+  BwdWork W = layout_bwd(*shape, d, workspace);
+  const Splits sp = wgrad_splits(B);
+  const size_t nsc = (size_t)B * classes;
+  cudaError_t e;
+
+  // upstream gradients per head (the alpha blend folds djoint into the two last heads)
+  const float* dS[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int h = 0; h < d.n_heads; ++h) dS[h] = dscores[h];
+  if (hang && djoint) {
+    joint_bwd_kernel<<<(int)((nsc + 255) / 256), 256, 0, st>>>(dscores[2], dscores[5], djoint, params->alpha, W.dS[2], W.dS[5], nsc);
+    DTA_CHECK_LAUNCH(ctx, "joint_bwd");
+    dS[2] = W.dS[2]; dS[5] = W.dS[5];
+    if (grads->alpha) {
+      alpha_grad_kernel<<<1, 1024, 0, st>>>(djoint, L.s3[0], L.s3[1], params->alpha, nsc, grads->alpha);
+      DTA_CHECK_LAUNCH(ctx, "alpha_grad");
+    }
+  } else if (hang && grads->alpha) {
+    cudaMemsetAsync(grads->alpha, 0, sizeof(double), st);
+  }
+  auto head_ds = [&](int g, int k) -> const float* {
+    if (vanilla) return k == 2 ? dS[0] : nullptr;
+    return dS[g * 3 + k];
+  };
+
+  // dgrad weight tables
+  for (int k = 1; k < 3; ++k) {
+    Ptr2 w{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}};
+    pack_conv_wd_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, kC[k], kC[k - 1], 0, W.wd[k]);
+    DTA_CHECK_LAUNCH(ctx, "pack_conv_wd");
+  }
+  if (dx) {
+    Ptr2 w{{params->branch[0].conv[0].conv_w, nb > 1 ? params->branch[1].conv[0].conv_w : nullptr}};
+    pack_conv_wd_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, 32, bands, 1, W.wd[0]);
+    DTA_CHECK_LAUNCH(ctx, "pack_conv_wd");
+  }
+
+  // zero-fill gradients that are only partially written (dead Conv1d taps) or may stay unreached
+  for (int g = 0; g < nb; ++g) {
+    const dta_branch& gb = grads->branch[g];
+    for (int k = 0; k < 3; ++k) {
+      if (d.btype[g] == BR_SPECTRAL) {
+        const int ks = k == 0 ? 3 : (k == 1 ? 5 : 7);
+        if (gb.attn[k].w0) cudaMemsetAsync(gb.attn[k].w0, 0, sizeof(float) * kC[k] * kC[k] * ks, st);
+        if (gb.attn[k].w1) cudaMemsetAsync(gb.attn[k].w1, 0, sizeof(float) * kC[k] * kC[k] * ks, st);
+      }
+      const int F = d.btype[g] == BR_SPECTRAL ? kC[k] : (d.btype[g] == BR_SPATIAL ? 4 * kC[k] : 512);
+      if (head_ds(g, k) == nullptr) {
+        if (gb.fc_w[k]) cudaMemsetAsync(gb.fc_w[k], 0, sizeof(float) * classes * F, st);
+        if (gb.fc_b[k]) cudaMemsetAsync(gb.fc_b[k], 0, sizeof(float) * classes, st);
+      }
+    }
+  }
+
+  auto bn_grads = [&](int k) {
+    BnGrads g{};
+    for (int b = 0; b < nb; ++b) {
+      g.dgamma[b] = grads->branch[b].conv[k].bn_w; g.dbeta[b] = grads->branch[b].conv[k].bn_b;
+      g.dconv_b[b] = grads->branch[b].conv[k].conv_b;
+    }
+    return g;
+  };
+  auto bn_bwd = [&](int k) -> int {
+    const int ctot = nb * kC[k];
+    bn_bwd_finalize_kernel<<<(ctot * 32 + 255) / 256, 256, 0, st>>>(W.bnrows, B, nb, kC[k], (double)B * kHWpre[k], bn_params(params, d, k),
+                                                                    L.bn_mean[k], L.bn_istd[k], shape->training, bn_grads(k), W.k0[k], W.k1[k], W.k2[k]);
+    DTA_CHECK_LAUNCH(ctx, "bn_bwd_finalize");
+    return DTA_OK;
+  };
+  // small parameter gradients of one attention block + head, reduced over the batch
+  auto attn_param_grads = [&](int k) -> int {
+    const int C = kC[k], ld = kProwLd[k];
+    for (int g = 0; g < nb; ++g) {
+      const dta_branch& gb = grads->branch[g];
+      const float* prow = W.prow + (size_t)g * ld;
+      const size_t prow_ld = (size_t)nb * ld;
+      const float* att = L.att[k] + (size_t)g * 3 * kAttRow[k];
+      const size_t att_ld = (size_t)nb * 3 * kAttRow[k];
+      if (d.btype[g] == BR_SPECTRAL) {
+        const int ks = k == 0 ? 3 : (k == 1 ? 5 : 7);
+        dim3 grid((C + 15) / 16, (C + 15) / 16), blk(16, 16);
+        // dW2[i][j][mid] = sum_b du2[b][i] * h[b][j];  dW1[i][j][mid] = sum_b du1[b][i] * g[b][j]
+        if (gb.attn[k].w1) { outer_sum_kernel<<<grid, blk, 0, st>>>(prow, prow_ld, att + kAttRow[k], att_ld, B, C, C, gb.attn[k].w1 + ks / 2, (size_t)C * ks, ks); DTA_CHECK_LAUNCH(ctx, "outer_sum"); }
+        if (gb.attn[k].w0) { outer_sum_kernel<<<grid, blk, 0, st>>>(prow + C, prow_ld, att, att_ld, B, C, C, gb.attn[k].w0 + ks / 2, (size_t)C * ks, ks); DTA_CHECK_LAUNCH(ctx, "outer_sum"); }
+        if (gb.attn[k].b1) { colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(prow, prow_ld, B, C, gb.attn[k].b1, 1); DTA_CHECK_LAUNCH(ctx, "colsum"); }
+        if (gb.attn[k].b0) { colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(prow + C, prow_ld, B, C, gb.attn[k].b0, 1); DTA_CHECK_LAUNCH(ctx, "colsum"); }
+      } else if (d.btype[g] == BR_SPATIAL) {
+        const int ks = k == 0 ? 7 : (k == 1 ? 5 : 3), kk = ks * ks;
+        auto cs = [&](const float* src, int n, float* dst) -> int {
+          if (!dst) return DTA_OK;
+          colsum_kernel<<<(n + 31) / 32, dim3(32, 8), 0, st>>>(src, prow_ld, B, n, dst, 1);
+          DTA_CHECK_LAUNCH(ctx, "colsum");
+          return DTA_OK;
+        };
+        int r;
+        if ((r = cs(prow, kk, gb.attn[k].w0)) || (r = cs(prow + kk, 1, gb.attn[k].b0)) || (r = cs(prow + kk + 1, kk, gb.attn[k].w1)) ||
+            (r = cs(prow + 2 * kk + 1, 1, gb.attn[k].b1)) || (r = cs(prow + 2 * kk + 2, C, gb.attn[k].pool_w)) ||
+            (r = cs(prow + 2 * kk + 2 + C, 1, gb.attn[k].pool_b)))
+          return r;
+      }
+      const float* ds = head_ds(g, k);
+      if (ds != nullptr && (d.btype[g] != BR_NONE || k == 2)) {
+        const int F = d.btype[g] == BR_SPECTRAL ? C : (d.btype[g] == BR_SPATIAL ? 4 * C : 512);
+        const float* feat = L.feat[k] + (size_t)g * kFeatLd[k];
+        if (gb.fc_w[k]) {
+          dim3 grid((F + 15) / 16, (classes + 15) / 16), blk(16, 16);
+          outer_sum_kernel<<<grid, blk, 0, st>>>(ds, classes, feat, (size_t)nb * kFeatLd[k], B, classes, F, gb.fc_w[k], F, 1);
+          DTA_CHECK_LAUNCH(ctx, "outer_sum");
+        }
+        if (gb.fc_b[k]) { colsum_kernel<<<(classes + 31) / 32, dim3(32, 8), 0, st>>>(ds, classes, B, classes, gb.fc_b[k], 1); DTA_CHECK_LAUNCH(ctx, "colsum"); }
+      }
+    }
+    return DTA_OK;
+  };
+  auto attn_prm = [&](int k) {
+    AttnParams a = attn_params(params, L, d, k, vanilla && k == 2);
+    return a;
+  };
+  auto ds_ptrs = [&](int k) {
+    Ptr2 p{{nullptr, nullptr}};
+    for (int g = 0; g < nb; ++g) p.p[g] = head_ds(g, k);
+    return p;
+  };
+  auto reduce_w = [&](int k, int cin) -> int {
+    MutPtr2 dw{{grads->branch[0].conv[k].conv_w, nb > 1 ? grads->branch[1].conv[k].conv_w : nullptr}};
+    const size_t per_branch = (size_t)kC[k] * cin * 9;
+    wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W.wpart, sp.n[k], 1, per_branch * nb, dw, per_branch);
+    DTA_CHECK_LAUNCH(ctx, "wgrad_reduce");
+    return DTA_OK;
+  };
+
+  // ---- block 3 ----
+  {
+    auto kern = attn_bwd_kernel<128, 5, true>;
+    const size_t sm = attn_bwd_smem<128, 5, true>(classes);
+    allow_smem(kern, sm);
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], L.bn_mean[2], L.bn_istd[2], attn_prm(2), classes, L.att[2], L.feat[2],
+                                              ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow);
+    DTA_CHECK_LAUNCH(ctx, "attn_bwd<3>");
+    if ((rc = attn_param_grads(2)) != DTA_OK) return rc;
+    if ((rc = bn_bwd(2)) != DTA_OK) return rc;
+    ConvSrc dz = src_dz(W.da[2], L.z[2], 128, nb * 128, 25, W.k0[2], W.k1[2], W.k2[2]);
+    ConvSrc in = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
+    e = launch_wgrad<5, 32, 128, 8>(in, dz, W.wpart, B, sp.n[2], sp.per[2], nb, st);
+    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 wgrad: ") + cudaGetErrorString(e));
+    ctx->launches++;
+    if ((rc = reduce_w(2, 64)) != DTA_OK) return rc;
+    e = launch_fprop<5, 4, 4, 8, 64, 8>(dz, W.wd[2], Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, nullptr, B, nb, st, nullptr);
+    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 dgrad: ") + cudaGetErrorString(e));
+    ctx->launches++;
+  }
+  // ---- block 2 ----
+  {
+    auto kern = attn_bwd_kernel<64, 11, true>;
+    const size_t sm = attn_bwd_smem<64, 11, true>(classes);
+    allow_smem(kern, sm);
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], L.bn_mean[1], L.bn_istd[1], attn_prm(1), classes, L.att[1], L.feat[1],
+                                              ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow);
+    DTA_CHECK_LAUNCH(ctx, "attn_bwd<2>");
+    if ((rc = attn_param_grads(1)) != DTA_OK) return rc;
+    if ((rc = bn_bwd(1)) != DTA_OK) return rc;
+    ConvSrc dz = src_dz(W.da[1], L.z[1], 64, nb * 64, 121, W.k0[1], W.k1[1], W.k2[1]);
+    ConvSrc in = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
+    e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[1], sp.per[1], nb, st);
+    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 wgrad: ") + cudaGetErrorString(e));
+    ctx->launches++;
+    if ((rc = reduce_w(1, 32)) != DTA_OK) return rc;
+    e = launch_fprop<11, 1, 8, 4, 32, 16>(dz, W.wd[1], Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, nullptr, B, nb, st, nullptr);
+    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 dgrad: ") + cudaGetErrorString(e));
+    ctx->launches++;
+  }
+  // ---- block 1 ----
+  {
+    auto kern = attn_bwd_kernel<32, 11, false>;
+    const size_t sm = attn_bwd_smem<32, 11, false>(classes);
+    allow_smem(kern, sm);
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], L.bn_mean[0], L.bn_istd[0], attn_prm(0), classes, L.att[0], L.feat[0],
+                                              ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow);
+    DTA_CHECK_LAUNCH(ctx, "attn_bwd<1>");
+    if ((rc = attn_param_grads(0)) != DTA_OK) return rc;
+    if ((rc = bn_bwd(0)) != DTA_OK) return rc;
+    ConvSrc dz = src_dz(W.da[0], L.z[0], nb * 32, nb * 32, 121, W.k0[0], W.k1[0], W.k2[0]);
+    ConvSrc in = src_raw(x, bands, kHW);
+    if (nb == 2) e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
+    else e = launch_wgrad<11, 32, 32, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
+    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv1 wgrad: ") + cudaGetErrorString(e));
+    ctx->launches++;
+    if ((rc = reduce_w(0, bands)) != DTA_OK) return rc;
+    if (dx) return fail(ctx, DTA_ERR_UNSUPPORTED, "gradient of the crops (dx) is not built yet; the reference feeds requires_grad=False inputs");
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("backward: ") + cudaGetErrorString(e));
+  return DTA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,460 @@
+// Per-crop fused stages between the convolutions: BatchNorm apply + ReLU + max-pool +
+// spectral / spatial attention gate + classifier head (forward), and their backward.
+// One CTA per (crop, branch).  Reference: conv_module.forward Hang2020.py:24-31,
+// spectral_attention.forward :149-168, spatial_attention.forward :105-124, Classifier :63-66.
+#pragma once
+#include "dta_common.cuh"
+
+namespace dta {
+
+constexpr int kAttnThreads = 128;
+
+// Per-branch parameter views used by the attention kernels (device pointers).
+struct AttnParams {
+  int btype[2];
+  // spectral: dense centre-tap matrices packed by pack_spectral_kernel:
+  //   w0d[i*C+j] = attention_conv1.weight[i][j][ks/2], w0t = transpose; same for w1
+  const float* w0d[2]; const float* w0t[2]; const float* w1d[2]; const float* w1t[2];
+  // spatial: raw reference tensors (1,1,ks,ks)
+  const float* st0[2]; const float* st1[2];
+  const float* b0[2]; const float* b1[2];
+  const float* pool_w[2]; const float* pool_b[2];
+  const float* fc_w[2]; const float* fc_b[2];   // head; nullptr = no head at this block
+};
+
+template <int C, int SPRE, bool POOL>
+struct AttnCfg {
+  static constexpr int S = POOL ? SPRE / 2 : SPRE;
+  static constexpr int HW = S * S;
+  static constexpr int HWPRE = SPRE * SPRE;
+  static constexpr int KS_SPATIAL = (C == 32) ? 7 : (C == 64 ? 5 : 3);   // Hang2020.py:77-82
+  static constexpr int WIN = (C == 32) ? 4 : (C == 64 ? 2 : 1);         // Hang2020.py:91-99
+  static constexpr int FEAT_SPATIAL = 4 * C;                             // 128 / 256 / 512
+  static constexpr int ROW = (C > HW) ? C : HW;   // stride of one vector in the saved attention row
+  static constexpr int ATT_LD = 3 * ROW;
+  static constexpr int FEAT_LD = 4 * C;
+};
+
+// Build r = [maxpool2x2](relu(z*scale+shift)) in shared memory (and optionally the argmax
+// slot of every pooled cell, first-max rule of ATen max_pool2d).
+template <int C, int SPRE, bool POOL>
+__device__ __forceinline__ void build_r(const float* __restrict__ zsrc, const float* __restrict__ scale,
+                                        const float* __restrict__ shift, float* s_z, float* s_r,
+                                        unsigned char* s_arg) {
+  using Cfg = AttnCfg<C, SPRE, POOL>;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < C * Cfg::HWPRE; i += kAttnThreads) s_z[i] = __ldg(zsrc + i);
+  __syncthreads();
+  if (POOL) {
+    for (int i = tid; i < C * Cfg::HW; i += kAttnThreads) {
+      const int c = i / Cfg::HW, p = i - c * Cfg::HW;
+      const int y = p / Cfg::S, x = p - y * Cfg::S;
+      const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+      float best = -INFINITY;
+      int arg = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = fmaxf(fmaf(s_z[c * Cfg::HWPRE + (2 * y + (k >> 1)) * SPRE + 2 * x + (k & 1)], sc, sh), 0.f);
+        if (a > best) { best = a; arg = k; }
+      }
+      s_r[i] = best;
+      if (s_arg != nullptr) s_arg[i] = (unsigned char)arg;
+    }
+  } else {
+    for (int i = tid; i < C * Cfg::HW; i += kAttnThreads) {
+      const int c = i / Cfg::HW;
+      s_r[i] = fmaxf(fmaf(s_z[i], __ldg(scale + c), __ldg(shift + c)), 0.f);
+    }
+  }
+  __syncthreads();
+}
+
+// k x k "same" stencil on an S x S plane held in shared memory (zero padding).
+template <int S, int KS>
+__device__ __forceinline__ float stencil_at(const float* s_plane, const float* __restrict__ w, int y, int x) {
+  float acc = 0.f;
+#pragma unroll
+  for (int u = 0; u < KS; ++u) {
+    const int yy = y + u - KS / 2;
+    if (yy < 0 || yy >= S) continue;
+#pragma unroll
+    for (int v = 0; v < KS; ++v) {
+      const int xx = x + v - KS / 2;
+      if (xx < 0 || xx >= S) continue;
+      acc = fmaf(__ldg(w + u * KS + v), s_plane[yy * S + xx], acc);
+    }
+  }
+  return acc;
+}
+
+// ------------------------------------------------------------------------------ forward
+template <int C, int SPRE, bool POOL>
+__global__ void __launch_bounds__(kAttnThreads)
+attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __restrict__ scale,
+                const float* __restrict__ shift, AttnParams prm, int classes,
+                float* __restrict__ att /*[B][G][ATT_LD]*/, float* __restrict__ feat /*[B][G][FEAT_LD]*/,
+                MutPtr2 scores /*per branch [B][classes]*/) {
+  using Cfg = AttnCfg<C, SPRE, POOL>;
+  constexpr int S = Cfg::S, HW = Cfg::HW;
+  extern __shared__ __align__(16) float smem[];
+  float* s_z = smem;                       // C*HWPRE
+  float* s_r = POOL ? (s_z + C * Cfg::HWPRE) : s_z;   // in-place when there is no pooling
+  float* s_v = s_r + C * HW;               // 3*ROW vectors
+  float* s_feat = s_v + 3 * Cfg::ROW;      // FEAT_LD
+
+  const int b = blockIdx.x, g = blockIdx.y, G = gridDim.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int btype = prm.btype[g];
+
+  build_r<C, SPRE, POOL>(z + ((size_t)b * G + g) * C * Cfg::HWPRE, scale + g * C, shift + g * C, s_z, s_r, nullptr);
+
+  float* att_row = att + ((size_t)b * G + g) * Cfg::ATT_LD;
+  float* feat_row = feat + ((size_t)b * G + g) * Cfg::FEAT_LD;
+  int F = 0;
+  if (btype == BR_SPECTRAL) {
+    float* s_g = s_v; float* s_h = s_v + Cfg::ROW; float* s_s = s_v + 2 * Cfg::ROW;
+    for (int c = warp; c < C; c += kAttnThreads / 32) {
+      float a = 0.f;
+      for (int p = lane; p < HW; p += 32) a += s_r[c * HW + p];
+      a = warp_sum(a);
+      if (lane == 0) s_g[c] = a / (float)HW;
+    }
+    __syncthreads();
+    for (int i = tid; i < C; i += kAttnThreads) {
+      float a = __ldg(prm.b0[g] + i);
+      const float* w = prm.w0t[g];
+      for (int j = 0; j < C; ++j) a = fmaf(__ldg(w + j * C + i), s_g[j], a);
+      s_h[i] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    for (int i = tid; i < C; i += kAttnThreads) {
+      float a = __ldg(prm.b1[g] + i);
+      const float* w = prm.w1t[g];
+      for (int j = 0; j < C; ++j) a = fmaf(__ldg(w + j * C + i), s_h[j], a);
+      s_s[i] = sigmoidf_acc(a);
+    }
+    __syncthreads();
+    for (int c = warp; c < C; c += kAttnThreads / 32) {
+      const float sv = s_s[c];
+      float a = 0.f;
+      for (int p = lane; p < HW; p += 32) a += s_r[c * HW + p] * sv;
+      a = warp_sum(a);
+      if (lane == 0) s_feat[c] = a / (float)HW;
+    }
+    F = C;
+    for (int i = tid; i < C; i += kAttnThreads) {
+      att_row[i] = s_g[i]; att_row[Cfg::ROW + i] = s_h[i]; att_row[2 * Cfg::ROW + i] = s_s[i];
+    }
+  } else if (btype == BR_SPATIAL) {
+    constexpr int KS = Cfg::KS_SPATIAL;
+    float* s_q = s_v; float* s_t = s_v + Cfg::ROW; float* s_s = s_v + 2 * Cfg::ROW;
+    for (int p = tid; p < HW; p += kAttnThreads) {
+      float a = __ldg(prm.pool_b[g]);
+      const float* w = prm.pool_w[g];
+      for (int c = 0; c < C; ++c) a = fmaf(__ldg(w + c), s_r[c * HW + p], a);
+      s_q[p] = fmaxf(a, 0.f);
+    }
+    __syncthreads();
+    for (int p = tid; p < HW; p += kAttnThreads)
+      s_t[p] = fmaxf(stencil_at<S, KS>(s_q, prm.st0[g], p / S, p % S) + __ldg(prm.b0[g]), 0.f);
+    __syncthreads();
+    for (int p = tid; p < HW; p += kAttnThreads)
+      s_s[p] = sigmoidf_acc(stencil_at<S, KS>(s_t, prm.st1[g], p / S, p % S) + __ldg(prm.b1[g]));
+    __syncthreads();
+    constexpr int WIN = Cfg::WIN;
+    for (int f = tid; f < 4 * C; f += kAttnThreads) {
+      const int c = f >> 2, i = (f >> 1) & 1, j = f & 1;
+      float best = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < WIN; ++u)
+#pragma unroll
+        for (int v = 0; v < WIN; ++v) {
+          const int p = (i * WIN + u) * S + j * WIN + v;
+          best = fmaxf(best, s_r[c * HW + p] * s_s[p]);
+        }
+      s_feat[f] = best;
+    }
+    F = 4 * C;
+    for (int p = tid; p < HW; p += kAttnThreads) {
+      att_row[p] = s_q[p]; att_row[Cfg::ROW + p] = s_t[p]; att_row[2 * Cfg::ROW + p] = s_s[p];
+    }
+  } else {
+    // vanilla_CNN: flatten(r) feeds fc1 (Hang2020.py:50-51); only launched for block 3
+    for (int f = tid; f < C * HW; f += kAttnThreads) s_feat[f] = s_r[f];
+    F = C * HW;
+  }
+  __syncthreads();
+  for (int f = tid; f < F; f += kAttnThreads) feat_row[f] = s_feat[f];
+  const float* fw = prm.fc_w[g];
+  if (fw != nullptr) {
+    float* sc_out = scores.p[g] + (size_t)b * classes;
+    for (int cls = warp; cls < classes; cls += kAttnThreads / 32) {
+      float a = 0.f;
+      for (int f = lane; f < F; f += 32) a = fmaf(s_feat[f], __ldg(fw + (size_t)cls * F + f), a);
+      a = warp_sum(a);
+      if (lane == 0) sc_out[cls] = a + __ldg(prm.fc_b[g] + cls);
+    }
+  }
+}
+
+template <int C, int SPRE, bool POOL>
+constexpr size_t attn_fwd_smem() {
+  using Cfg = AttnCfg<C, SPRE, POOL>;
+  return sizeof(float) * ((POOL ? C * Cfg::HWPRE : 0) + C * Cfg::HW + 3 * Cfg::ROW + Cfg::FEAT_LD);
+}
+
+// ------------------------------------------------------------------------------ backward
+// Row layout of the per-crop parameter-gradient partials written by attn_bwd_kernel:
+//   spectral: [du2 (C) | du1 (C)]
+//   spatial : [dA1 (KS*KS) | db_a1 | dA2 (KS*KS) | db_a2 | dpool_w (C) | dpool_b]
+template <int C, int SPRE, bool POOL>
+struct AttnBwdRow {
+  using Cfg = AttnCfg<C, SPRE, POOL>;
+  static constexpr int KK = Cfg::KS_SPATIAL * Cfg::KS_SPATIAL;
+  static constexpr int SPATIAL_LEN = 2 * KK + 2 + C + 1;
+  static constexpr int SPECTRAL_LEN = 2 * C;
+  static constexpr int LEN = SPATIAL_LEN > SPECTRAL_LEN ? SPATIAL_LEN : SPECTRAL_LEN;
+  static constexpr int LD = (LEN + 3) / 4 * 4;
+};
+
+template <int C, int SPRE, bool POOL>
+__global__ void __launch_bounds__(kAttnThreads)
+attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                const float* __restrict__ mean, const float* __restrict__ istd, AttnParams prm, int classes,
+                const float* __restrict__ att, const float* __restrict__ feat_unused,
+                Ptr2 dscores /*per branch [B][classes] or null*/, const float* __restrict__ dout /*[B][G][C][HW] or null*/,
+                float* __restrict__ da /*[B][G*C][HWPRE]*/, float* __restrict__ bnrow /*[B][G][2C]*/,
+                float* __restrict__ prow /*[B][G][ROW_LD]*/) {
+  using Cfg = AttnCfg<C, SPRE, POOL>;
+  using Row = AttnBwdRow<C, SPRE, POOL>;
+  constexpr int S = Cfg::S, HW = Cfg::HW, HWPRE = Cfg::HWPRE;
+  extern __shared__ __align__(16) float smem[];
+  float* s_z = smem;                       // C*HWPRE raw conv output
+  float* s_r = s_z + C * HWPRE;            // C*HW
+  float* s_D = s_r + C * HW;               // C*HW  gradient wrt gated output, then wrt r
+  float* s_v = s_D + C * HW;               // 3*ROW saved attention vectors
+  float* s_w = s_v + 3 * Cfg::ROW;         // 4*ROW work vectors
+  float* s_dfeat = s_w + 4 * Cfg::ROW;     // FEAT_LD
+  float* s_ds = s_dfeat + Cfg::FEAT_LD;    // classes (rounded up by the launcher)
+  unsigned char* s_arg = reinterpret_cast<unsigned char*>(s_ds + ((classes + 3) / 4) * 4);  // C*HW
+
+  const int b = blockIdx.x, g = blockIdx.y, G = gridDim.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int btype = prm.btype[g];
+  const float* sc = scale + g * C;
+  const float* sh = shift + g * C;
+  (void)feat_unused;
+
+  build_r<C, SPRE, POOL>(z + ((size_t)b * G + g) * C * HWPRE, sc, sh, s_z, s_r, POOL ? s_arg : nullptr);
+
+  const float* att_row = att + ((size_t)b * G + g) * Cfg::ATT_LD;
+  for (int i = tid; i < 3 * Cfg::ROW; i += kAttnThreads) s_v[i] = __ldg(att_row + i);
+  const float* dsc = dscores.p[g];
+  const bool has_head = (dsc != nullptr) && (prm.fc_w[g] != nullptr);
+  if (has_head)
+    for (int i = tid; i < classes; i += kAttnThreads) s_ds[i] = __ldg(dsc + (size_t)b * classes + i);
+  __syncthreads();
+
+  const int F = (btype == BR_SPECTRAL) ? C : (btype == BR_SPATIAL ? 4 * C : (has_head ? C * HW : 0));
+  // gradient of the head features: dfeat = Wc^T dscores   (Classifier, Hang2020.py:64)
+  for (int f = tid; f < F; f += kAttnThreads) {
+    float a = 0.f;
+    if (has_head) {
+      const float* fw = prm.fc_w[g];
+      for (int cls = 0; cls < classes; ++cls) a = fmaf(s_ds[cls], __ldg(fw + (size_t)cls * F + f), a);
+    }
+    s_dfeat[f] = a;
+  }
+  // upstream gradient of the gated feature map from the next conv's dgrad
+  const float* dsrc = dout ? dout + ((size_t)b * G + g) * C * HW : nullptr;
+  for (int i = tid; i < C * HW; i += kAttnThreads) s_D[i] = dsrc ? __ldg(dsrc + i) : 0.f;
+  __syncthreads();
+
+  float* prow_row = prow + ((size_t)b * G + g) * Row::LD;
+
+  if (btype == BR_SPECTRAL) {
+    const float* s_g = s_v; const float* s_h = s_v + Cfg::ROW; const float* s_s = s_v + 2 * Cfg::ROW;
+    float* s_dsv = s_w; float* s_du2 = s_w + Cfg::ROW; float* s_du1 = s_w + 2 * Cfg::ROW; float* s_dg = s_w + 3 * Cfg::ROW;
+    (void)s_g;
+    // D += dfeat/HW (mean over HW, global_spectral_pool :7-12);  ds[c] = sum_p D*r
+    for (int c = warp; c < C; c += kAttnThreads / 32) {
+      const float df = s_dfeat[c] / (float)HW;
+      float a = 0.f;
+      for (int p = lane; p < HW; p += 32) {
+        const float d = s_D[c * HW + p] + df;
+        s_D[c * HW + p] = d;
+        a = fmaf(d, s_r[c * HW + p], a);
+      }
+      a = warp_sum(a);
+      if (lane == 0) s_dsv[c] = a;
+    }
+    __syncthreads();
+    for (int i = tid; i < C; i += kAttnThreads) {
+      const float sv = s_s[i];
+      s_du2[i] = s_dsv[i] * sv * (1.f - sv);
+    }
+    __syncthreads();
+    for (int j = tid; j < C; j += kAttnThreads) {
+      float a = 0.f;
+      const float* w = prm.w1d[g];
+      for (int i = 0; i < C; ++i) a = fmaf(__ldg(w + i * C + j), s_du2[i], a);
+      s_du1[j] = (s_h[j] > 0.f) ? a : 0.f;
+    }
+    __syncthreads();
+    for (int j = tid; j < C; j += kAttnThreads) {
+      float a = 0.f;
+      const float* w = prm.w0d[g];
+      for (int i = 0; i < C; ++i) a = fmaf(__ldg(w + i * C + j), s_du1[i], a);
+      s_dg[j] = a / (float)HW;
+    }
+    __syncthreads();
+    for (int i = tid; i < C * HW; i += kAttnThreads) {
+      const int c = i / HW;
+      s_D[i] = fmaf(s_D[i], s_s[c], s_dg[c]);
+    }
+    for (int i = tid; i < C; i += kAttnThreads) { prow_row[i] = s_du2[i]; prow_row[C + i] = s_du1[i]; }
+  } else if (btype == BR_SPATIAL) {
+    constexpr int KS = Cfg::KS_SPATIAL, KK = KS * KS, WIN = Cfg::WIN;
+    const float* s_q = s_v; const float* s_t = s_v + Cfg::ROW; const float* s_s = s_v + 2 * Cfg::ROW;
+    float* s_dv2 = s_w; float* s_dv1 = s_w + Cfg::ROW; float* s_dq = s_w + 2 * Cfg::ROW;
+    // route head-feature gradient through the class max-pool (first-max rule)
+    for (int f = tid; f < 4 * C; f += kAttnThreads) {
+      const int c = f >> 2, i = (f >> 1) & 1, j = f & 1;
+      float best = -INFINITY; int barg = 0;
+#pragma unroll
+      for (int u = 0; u < WIN; ++u)
+#pragma unroll
+        for (int v = 0; v < WIN; ++v) {
+          const int p = (i * WIN + u) * S + j * WIN + v;
+          const float o = s_r[c * HW + p] * s_s[p];
+          if (o > best) { best = o; barg = p; }
+        }
+      s_D[c * HW + barg] += s_dfeat[f];   // windows are disjoint: no race
+    }
+    __syncthreads();
+    // ds[p] = sum_c D*r ; dv2 = ds * s(1-s)
+    for (int p = tid; p < HW; p += kAttnThreads) {
+      float a = 0.f;
+      for (int c = 0; c < C; ++c) a = fmaf(s_D[c * HW + p], s_r[c * HW + p], a);
+      const float sv = s_s[p];
+      s_dv2[p] = a * sv * (1.f - sv);
+    }
+    __syncthreads();
+    // dt = A2^T * dv2 (transposed stencil); dv1 = dt * (t>0)
+    for (int p = tid; p < HW; p += kAttnThreads) {
+      const int y = p / S, x = p % S;
+      float a = 0.f;
+      for (int u = 0; u < KS; ++u) {
+        const int yy = y - u + KS / 2;
+        if (yy < 0 || yy >= S) continue;
+        for (int v = 0; v < KS; ++v) {
+          const int xx = x - v + KS / 2;
+          if (xx < 0 || xx >= S) continue;
+          a = fmaf(__ldg(prm.st1[g] + u * KS + v), s_dv2[yy * S + xx], a);
+        }
+      }
+      s_dv1[p] = (s_t[p] > 0.f) ? a : 0.f;
+    }
+    __syncthreads();
+    for (int p = tid; p < HW; p += kAttnThreads) {
+      const int y = p / S, x = p % S;
+      float a = 0.f;
+      for (int u = 0; u < KS; ++u) {
+        const int yy = y - u + KS / 2;
+        if (yy < 0 || yy >= S) continue;
+        for (int v = 0; v < KS; ++v) {
+          const int xx = x - v + KS / 2;
+          if (xx < 0 || xx >= S) continue;
+          a = fmaf(__ldg(prm.st0[g] + u * KS + v), s_dv1[yy * S + xx], a);
+        }
+      }
+      s_dq[p] = (s_q[p] > 0.f) ? a : 0.f;
+    }
+    __syncthreads();
+    // stencil / bias / channel-pool parameter partials for this crop
+    for (int e = tid; e < 2 * KK + 2; e += kAttnThreads) {
+      const bool second = e >= KK + 1;
+      const int k = second ? e - (KK + 1) : e;
+      const float* dv = second ? s_dv2 : s_dv1;
+      const float* src = second ? s_t : s_q;
+      float a = 0.f;
+      if (k == KK) {
+        for (int p = 0; p < HW; ++p) a += dv[p];
+      } else {
+        const int u = k / KS, v = k % KS;
+        for (int y = 0; y < S; ++y) {
+          const int yy = y + u - KS / 2;
+          if (yy < 0 || yy >= S) continue;
+          for (int x = 0; x < S; ++x) {
+            const int xx = x + v - KS / 2;
+            if (xx < 0 || xx >= S) continue;
+            a = fmaf(dv[y * S + x], src[yy * S + xx], a);
+          }
+        }
+      }
+      prow_row[e] = a;
+    }
+    for (int c = warp; c < C; c += kAttnThreads / 32) {
+      float a = 0.f;
+      for (int p = lane; p < HW; p += 32) a = fmaf(s_dq[p], s_r[c * HW + p], a);
+      a = warp_sum(a);
+      if (lane == 0) prow_row[2 * KK + 2 + c] = a;
+    }
+    if (warp == 0) {
+      float a = 0.f;
+      for (int p = lane; p < HW; p += 32) a += s_dq[p];
+      a = warp_sum(a);
+      if (lane == 0) prow_row[2 * KK + 2 + C] = a;
+    }
+    __syncthreads();
+    // dr = D*s + pool_w[c]*dq
+    for (int i = tid; i < C * HW; i += kAttnThreads) {
+      const int c = i / HW, p = i - c * HW;
+      s_D[i] = fmaf(s_D[i], s_s[p], __ldg(prm.pool_w[g] + c) * s_dq[p]);
+    }
+  } else {
+    // vanilla: flatten feeds fc1 at block 3; blocks 1/2 pass the upstream gradient through
+    if (has_head)
+      for (int i = tid; i < C * HW; i += kAttnThreads) s_D[i] += s_dfeat[i];
+  }
+  __syncthreads();
+
+  // route through max-pool (argmax) and ReLU; emit da and the BatchNorm-backward partials
+  float* da_out = da + ((size_t)b * G + g) * C * HWPRE;
+  float* bn_row = bnrow + ((size_t)b * G + g) * 2 * C;
+  for (int c = warp; c < C; c += kAttnThreads / 32) {
+    const float scv = __ldg(sc + c), shv = __ldg(sh + c);
+    const float mu = __ldg(mean + g * C + c), is = __ldg(istd + g * C + c);
+    float s1 = 0.f, s2 = 0.f;
+    for (int pp = lane; pp < HWPRE; pp += 32) {
+      const float zv = s_z[c * HWPRE + pp];
+      const float a = fmaf(zv, scv, shv);
+      float dv = 0.f;
+      if (POOL) {
+        const int yy = pp / SPRE, xx = pp - yy * SPRE;
+        if (yy < 2 * S && xx < 2 * S) {
+          const int cell = (yy >> 1) * S + (xx >> 1);
+          const int slot = ((yy & 1) << 1) | (xx & 1);
+          if (s_arg[c * HW + cell] == slot && a > 0.f) dv = s_D[c * HW + cell];
+        }
+      } else {
+        if (a > 0.f) dv = s_D[c * HW + pp];
+      }
+      da_out[c * HWPRE + pp] = dv;
+      s1 += dv;
+      s2 = fmaf(dv, (zv - mu) * is, s2);
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (lane == 0) { bn_row[c] = s1; bn_row[C + c] = s2; }
+  }
+}
+
+template <int C, int SPRE, bool POOL>
+size_t attn_bwd_smem(int classes) {
+  using Cfg = AttnCfg<C, SPRE, POOL>;
+  const size_t floats = (size_t)C * Cfg::HWPRE + 2 * C * Cfg::HW + 7 * Cfg::ROW + Cfg::FEAT_LD + ((classes + 3) / 4) * 4;
+  return floats * sizeof(float) + (size_t)C * Cfg::HW;
+}
+
+}  // namespace dta

@@ -1,0 +1,245 @@
+// Small kernels around the hot stages: parameter packing, BatchNorm statistics
+// finalisation (forward and backward), deterministic batch reductions for the small
+// parameter gradients, and the alpha blend of Hang2020.forward (Hang2020.py:256-261).
+#pragma once
+#include "dta_common.cuh"
+
+namespace dta {
+
+// Wp[g][ci][tap][co]: forward weight table.  merged=1: one group whose output channels are
+// the concatenation of both branches (conv1 reads the same crops for both branches).
+__global__ void pack_conv_w_kernel(Ptr2 w, int nb, int cout_b, int cin, int merged, float* __restrict__ wp) {
+  const size_t per = (size_t)cout_b * cin * 9;
+  const size_t total = per * nb;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int br = (int)(i / per);
+    const size_t r = i - (size_t)br * per;
+    const int co = (int)(r / ((size_t)cin * 9));
+    const int rr = (int)(r - (size_t)co * cin * 9);
+    const int ci = rr / 9, tap = rr - ci * 9;
+    const float v = __ldg(w.p[br] + r);
+    size_t o;
+    if (merged) o = ((size_t)ci * 9 + tap) * (nb * cout_b) + br * cout_b + co;
+    else o = (((size_t)br * cin + ci) * 9 + tap) * cout_b + co;
+    wp[o] = v;
+  }
+}
+
+// Wd[g][co][8-tap][ci]: the transposed + flipped table that turns the forward kernel into
+// the input-gradient kernel.  merged=1: single group with nb*cout_b "input" channels.
+__global__ void pack_conv_wd_kernel(Ptr2 w, int nb, int cout_b, int cin, int merged, float* __restrict__ wd) {
+  const size_t per = (size_t)cout_b * cin * 9;
+  const size_t total = per * nb;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int br = (int)(i / per);
+    const size_t r = i - (size_t)br * per;
+    const int co = (int)(r / ((size_t)cin * 9));
+    const int rr = (int)(r - (size_t)co * cin * 9);
+    const int ci = rr / 9, tap = rr - ci * 9;
+    const float v = __ldg(w.p[br] + r);
+    (void)merged;  // both cases index the "input" channel as br*cout_b+co
+    const size_t o = (((size_t)br * cout_b + co) * 9 + (8 - tap)) * cin + ci;
+    wd[o] = v;
+  }
+}
+
+// Dense centre taps of the Conv1d attention weights (C,C,ks): only tap ks/2 sees the length-1
+// sequence (Hang2020.py:146-147,155-158).  d[i*C+j] and its transpose t[j*C+i].
+__global__ void pack_spectral_kernel(const float* __restrict__ w, int C, int ks, float* __restrict__ d,
+                                     float* __restrict__ t) {
+  const int total = C * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / C, c = i - r * C;
+    const float v = __ldg(w + (size_t)i * ks + ks / 2);
+    d[i] = v;
+    t[c * C + r] = v;
+  }
+}
+
+struct BnParams {
+  const float* gamma[2];
+  const float* beta[2];
+  float* rm[2];
+  float* rv[2];
+  long long* nbt[2];
+  int c_per_branch;
+};
+
+// One warp per channel.  training: reduce the conv kernels' per-CTA partial sums in fp64,
+// produce mean / invstd / scale / shift and update the running statistics (momentum 0.1,
+// unbiased variance) exactly like nn.BatchNorm2d in train(); eval: use running statistics.
+__global__ void bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int nblk, int ctot,
+                                       double count, BnParams bn, int training, float* __restrict__ mean,
+                                       float* __restrict__ istd, float* __restrict__ scale, float* __restrict__ shift) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= ctot) return;
+  const int br = warp / bn.c_per_branch, c = warp - br * bn.c_per_branch;
+  float m, is;
+  if (training) {
+    double s = 0.0, q = 0.0;
+    for (int k = lane; k < nblk; k += 32) {
+      s += (double)part[((size_t)k * ctot + warp) * 2 + 0];
+      q += (double)part[((size_t)k * ctot + warp) * 2 + 1];
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    const double mu = s / count;
+    double var = q / count - mu * mu;
+    if (var < 0.0) var = 0.0;
+    m = (float)mu;
+    is = (float)(1.0 / sqrt(var + (double)kBnEps));
+    if (lane == 0) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      bn.rm[br][c] = (float)((1.0 - kBnMomentum) * (double)bn.rm[br][c] + kBnMomentum * mu);
+      bn.rv[br][c] = (float)((1.0 - kBnMomentum) * (double)bn.rv[br][c] + kBnMomentum * unbiased);
+      if (c == 0 && bn.nbt[br] != nullptr) bn.nbt[br][0] += 1;
+    }
+  } else {
+    m = bn.rm[br][c];
+    is = (float)(1.0 / sqrt((double)bn.rv[br][c] + (double)kBnEps));
+  }
+  if (lane == 0) {
+    const float sc = bn.gamma[br][c] * is;
+    mean[warp] = m;
+    istd[warp] = is;
+    scale[warp] = sc;
+    shift[warp] = bn.beta[br][c] - m * sc;
+  }
+}
+
+struct BnGrads {
+  float* dgamma[2];
+  float* dbeta[2];
+  float* dconv_b[2];
+};
+
+// One warp per channel.  rows[b][ctot*2] hold per-crop (sum da | sum da*zhat); reduce over
+// the batch in fp64 (fixed order), emit dgamma / dbeta / dbias and the coefficients of
+//   dz = k0*da + k1*z + k2     (train: k0 = gamma*istd, k1 = -k0*istd*dgamma/N,
+//                               k2 = -k0*dbeta/N - k1*mean;  eval: k1 = k2 = 0)
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, int G, int C, double count,
+                                       BnParams bn, const float* __restrict__ mean, const float* __restrict__ istd,
+                                       int training, BnGrads gr, float* __restrict__ k0, float* __restrict__ k1,
+                                       float* __restrict__ k2) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int ctot = G * C;
+  if (warp >= ctot) return;
+  const int g = warp / C, c = warp - g * C;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = lane; b < B; b += 32) {
+    const float* r = rows + ((size_t)b * G + g) * 2 * C;
+    s1 += (double)r[c];
+    s2 += (double)r[C + c];
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane != 0) return;
+  const int br = warp / bn.c_per_branch, cb = warp - br * bn.c_per_branch;
+  const double gam = bn.gamma[br][cb];
+  const double is = istd[warp], mu = mean[warp];
+  const double a = gam * is;
+  double b1 = 0.0, b2 = 0.0, dbias;
+  if (training) {
+    b1 = -a * is * s2 / count;
+    b2 = -a * s1 / count - b1 * mu;
+    dbias = 0.0;  // sum of dz over the batch vanishes identically under batch statistics
+  } else {
+    dbias = a * s1;
+  }
+  k0[warp] = (float)a;
+  k1[warp] = (float)b1;
+  k2[warp] = (float)b2;
+  if (gr.dgamma[br]) gr.dgamma[br][cb] = (float)s2;
+  if (gr.dbeta[br]) gr.dbeta[br][cb] = (float)s1;
+  if (gr.dconv_b[br]) gr.dconv_b[br][cb] = (float)dbias;
+}
+
+// out[j*ostride] = sum_b rows[b*ld + j], j < n.  Block = 32 columns x 8 batch slices.
+__global__ void colsum_kernel(const float* __restrict__ rows, size_t ld, int B, int n, float* __restrict__ out,
+                              int ostride) {
+  __shared__ float s[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  float a = 0.f;
+  if (j < n)
+    for (int b = threadIdx.y; b < B; b += 8) a += rows[(size_t)b * ld + j];
+  s[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s[k][threadIdx.x];
+    out[(size_t)j * ostride] = t;
+  }
+}
+
+// out[i*si + j*sj] = sum_b U[b*ldu + i] * V[b*ldv + j]  (i < ni, j < nj); 16x16 outputs per
+// block, batch walked in shared-memory tiles of 32.
+__global__ void outer_sum_kernel(const float* __restrict__ U, size_t ldu, const float* __restrict__ V, size_t ldv,
+                                 int B, int ni, int nj, float* __restrict__ out, size_t si, size_t sj) {
+  __shared__ float su[32][17];
+  __shared__ float sv[32][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 16 x 16
+  const int i0 = blockIdx.y * 16, j0 = blockIdx.x * 16;
+  const int t = ty * 16 + tx;
+  float acc = 0.f;
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    for (int e = t; e < 32 * 16; e += 256) {
+      const int bb = e >> 4, k = e & 15;
+      const int b = b0 + bb;
+      su[bb][k] = (b < B && i0 + k < ni) ? U[(size_t)b * ldu + i0 + k] : 0.f;
+      sv[bb][k] = (b < B && j0 + k < nj) ? V[(size_t)b * ldv + j0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int bb = 0; bb < 32; ++bb) acc = fmaf(su[bb][ty], sv[bb][tx], acc);
+    __syncthreads();
+  }
+  if (i0 + ty < ni && j0 + tx < nj) out[(size_t)(i0 + ty) * si + (size_t)(j0 + tx) * sj] = acc;
+}
+
+// joint = s_spec * float(w) + s_spat * float(1-w),  w = sigmoid(alpha) in fp64 (Hang2020.py:259-260)
+__global__ void joint_fwd_kernel(const float* __restrict__ spec, const float* __restrict__ spat,
+                                 const double* __restrict__ alpha, float* __restrict__ joint, size_t n) {
+  const double w = 1.0 / (1.0 + exp(-alpha[0]));
+  const float wf = (float)w, vf = (float)(1.0 - w);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    joint[i] = spec[i] * wf + spat[i] * vf;
+}
+
+// dS_spec = dscores_spec + djoint*w ; dS_spat = dscores_spat + djoint*(1-w)
+__global__ void joint_bwd_kernel(const float* __restrict__ dspec, const float* __restrict__ dspat,
+                                 const float* __restrict__ djoint, const double* __restrict__ alpha,
+                                 float* __restrict__ out_spec, float* __restrict__ out_spat, size_t n) {
+  const double w = 1.0 / (1.0 + exp(-alpha[0]));
+  const float wf = (float)w, vf = (float)(1.0 - w);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float dj = djoint[i];
+    out_spec[i] = (dspec ? dspec[i] : 0.f) + dj * wf;
+    out_spat[i] = (dspat ? dspat[i] : 0.f) + dj * vf;
+  }
+}
+
+// dalpha = w(1-w) * sum djoint * (s_spec - s_spat); single block, fixed-order fp64 tree.
+__global__ void alpha_grad_kernel(const float* __restrict__ djoint, const float* __restrict__ spec,
+                                  const float* __restrict__ spat, const double* __restrict__ alpha, size_t n,
+                                  double* __restrict__ dalpha) {
+  __shared__ double s[1024];
+  double a = 0.0;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) a += (double)(djoint[i] * spec[i]) - (double)(djoint[i] * spat[i]);
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double w = 1.0 / (1.0 + exp(-alpha[0]));
+    dalpha[0] = s[0] * w * (1.0 - w);
+  }
+}
+
+__global__ void fill_zero_kernel(float* __restrict__ p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
+}
+
+}  // namespace dta

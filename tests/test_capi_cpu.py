@@ -1,0 +1,102 @@
+"""CPU: the C-ABI library builds/loads and exports every symbol the header declares; host-side
+logic of the drop-in modules (state_dict contract, error behaviour) -- no compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import hang2020_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "dta_b200.h")).read()
+    return sorted(set(re.findall(r"\b(dta_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from deeptreeattention_b200 import _capi
+    path = _capi.build()
+    lib = ctypes.CDLL(path)
+    syms = header_symbols()
+    assert set(syms) == set(_capi.EXPORTS), (syms, _capi.EXPORTS)
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert _capi.lib().dta_abi_version() == 1
+
+
+def test_query_sizes_and_bad_shapes():
+    from deeptreeattention_b200 import _capi
+    s = _capi.query_sizes(_capi.NET_HANG2020, 1024, 369, 50, True)
+    assert s.n_heads == 6 and s.saved_bytes > 1024 * 118 * 1024 and s.workspace_bwd > 0
+    assert _capi.query_sizes(_capi.NET_VANILLA, 4, 3, 2, True).n_heads == 1
+    with pytest.raises(ValueError):
+        _capi.query_sizes(9, 4, 3, 2, True)
+    with pytest.raises(ValueError):
+        _capi.query_sizes(_capi.NET_HANG2020, 0, 3, 2, True)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu():
+    from deeptreeattention_b200 import _capi
+    with pytest.raises(_capi.DtaError) as e:
+        _capi.context(0)
+    assert "no CPU fallback" in str(e.value) or "no CUDA device" in str(e.value)
+
+
+@pytest.mark.parametrize("kind,cls", [("hang2020", "Hang2020"), ("spectral", "spectral_network"),
+                                      ("spatial", "spatial_network"), ("vanilla", "vanilla_CNN")])
+def test_state_dict_contract(kind, cls):
+    from deeptreeattention_b200 import Hang2020 as H
+    m = getattr(H, cls)(bands=369, classes=10)
+    sd = m.state_dict()
+    want = orc.param_shapes(kind, 369, 10)
+    assert list(sd.keys()) == [n for n, _, _ in want]
+    for n, shape, role in want:
+        assert tuple(sd[n].shape) == tuple(shape), n
+        if role == "alpha":
+            assert sd[n].dtype == torch.float64
+        elif role == "bn_nbt":
+            assert sd[n].dtype == torch.int64
+        else:
+            assert sd[n].dtype == torch.float32
+    m.load_state_dict(orc.init_params(kind, 369, 10, 0))
+
+
+def test_reference_api_surface_and_errors(tmp_path):
+    from deeptreeattention_b200 import Hang2020 as H
+    for name in ("global_spectral_pool", "conv_module", "vanilla_CNN", "Classifier", "spatial_attention",
+                 "spectral_attention", "spatial_network", "spectral_network", "Hang2020", "load_from_backbone"):
+        assert hasattr(H, name), name
+    with pytest.raises(ValueError):
+        H.spectral_attention(filters=48)
+    with pytest.raises(ValueError):
+        H.spatial_attention(filters=48)
+    assert H.global_spectral_pool(torch.ones(2, 3, 4, 4)).shape == (2, 3, 1)
+    m = H.Hang2020(bands=3, classes=10)
+    with pytest.raises(RuntimeError):
+        m(torch.randn(2, 3, 11, 11))          # no CPU path, must not silently fall back
+    # load_from_backbone: 10 -> 20 classes keeps every non-classifier tensor (tests/test_Hang2020.py:66-75)
+    path = str(tmp_path / "state_dict.pt")
+    torch.save(m.spectral_network.state_dict(), path)
+    m20 = H.load_from_backbone(state_dict=path, classes=20, bands=3)
+    assert m20.classifier3.fc1.weight.shape == (20, 128)
+    assert torch.equal(m20.conv1.conv_layer.weight, m.spectral_network.conv1.conv_layer.weight)
+    assert torch.equal(m20.attention_2.attention_conv1.weight, m.spectral_network.attention_2.attention_conv1.weight)
+
+
+def test_same_seed_same_init_as_torch_layers():
+    """Parameter containers are real torch.nn layers created in the reference's order, so a
+    seeded construction consumes the RNG identically (init under manual_seed(0))."""
+    from deeptreeattention_b200 import Hang2020 as H
+    torch.manual_seed(0)
+    a = H.spectral_network(5, 3).state_dict()
+    torch.manual_seed(0)
+    b = H.spectral_network(5, 3).state_dict()
+    for k in a:
+        assert torch.equal(a[k], b[k])
+    bound = 1.0 / (5 * 9) ** 0.5
+    assert float(a["conv1.conv_layer.weight"].abs().max()) <= bound

@@ -1,0 +1,143 @@
+"""GPU parity: the CUDA path (through the C ABI, via the drop-in modules) against (1) the
+golden vectors produced by the reference module and (2) the CPU oracle on seeded inputs.
+Tolerances (BASELINE.json north_star): scores within 1e-3 fp32 max-abs, identical argmax where
+the reference top-2 margin exceeds 1e-4; gradients 1e-3 relative to the tensor's max with an
+absolute floor of 1e-5 (conv biases under batch-stat BN have true gradient 0); BatchNorm
+running statistics 1e-5."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import hang2020_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-3
+MARGIN = 1e-4
+
+
+def _modules():
+    from deeptreeattention_b200 import Hang2020 as H
+    return {"hang2020": H.Hang2020, "spectral": H.spectral_network, "spatial": H.spatial_network,
+            "vanilla": H.vanilla_CNN}
+
+
+def run_cuda(kind, bands, classes, table, x, y, regime, training):
+    m = _modules()[kind](bands, classes)
+    m.load_state_dict(table)
+    m = m.cuda().train(training)
+    xd, yd = x.cuda(), y.cuda()
+    out = m(xd)
+    if kind == "hang2020":
+        heads, result = m.head_scores, out
+    elif kind == "vanilla":
+        heads, result = [out], out
+    else:
+        heads, result = out, out
+    loss = orc.loss_regime(regime, result, heads, yd)
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: (p.grad.detach().cpu() if p.grad is not None else None) for k, p in m.named_parameters()}
+    bufs = {k: v.detach().cpu() for k, v in m.state_dict().items() if orc.is_buffer(k)}
+    res = result[-1] if isinstance(result, list) else result
+    return float(loss), res.detach().cpu().numpy(), [h.detach().cpu().numpy() for h in heads], grads, bufs
+
+
+def assert_argmax(got, ref):
+    top2 = np.sort(ref, axis=1)[:, -2:]
+    safe = (top2[:, 1] - top2[:, 0]) > MARGIN
+    assert np.array_equal(got.argmax(1)[safe], ref.argmax(1)[safe]), "argmax differs outside the tie margin"
+
+
+@pytest.mark.parametrize("case", gu.cases(), ids=lambda c: c["name"])
+def test_cuda_matches_reference_golden(case):
+    gold = gu.load(case)
+    table, x, y = gu.build(case)
+    loss, res, heads, grads, bufs = run_cuda(case["kind"], case["bands"], case["classes"], table, x, y,
+                                             case["regime"], case["training"])
+    np.testing.assert_allclose(res, gold["result"], rtol=0, atol=SCORE_TOL)
+    assert_argmax(res, gold["result"])
+    for i, h in enumerate(heads):
+        np.testing.assert_allclose(h, gold[f"head{i}"], rtol=0, atol=SCORE_TOL)
+        assert_argmax(h, gold[f"head{i}"])
+    assert abs(loss - float(gold["loss"])) < 1e-3
+    for k, v in bufs.items():
+        np.testing.assert_allclose(v.numpy(), gold[f"buf/{k}"], rtol=1e-5, atol=1e-5)
+    gu.check_grads(gold, grads, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("kind,bands,classes,batch,regime,training", [
+    ("hang2020", 369, 50, 64, "R1", True),
+    ("hang2020", 369, 50, 33, "R2", True),
+    ("hang2020", 349, 7, 16, "R2", False),
+    ("spectral", 369, 20, 64, "R2", True),
+    ("spatial", 369, 20, 17, "R2", True),
+    ("vanilla", 3, 2, 4, "R1", True),
+    ("hang2020", 3, 10, 1, "R2", False),
+])
+def test_cuda_matches_oracle(kind, bands, classes, batch, regime, training):
+    torch.set_num_threads(8)
+    seed = 1000 + batch
+    table = orc.init_params(kind, bands, classes, seed, perturb_bn=True)
+    x, y = orc.make_inputs(batch, bands, classes, seed, "uniform" if batch % 2 == 0 else "normal")
+    rloss, rres, rheads, rgrads, rbufs = orc.step(kind, table, x, y, regime=regime, training=training)
+    rres = rres[-1] if isinstance(rres, list) else rres
+    loss, res, heads, grads, bufs = run_cuda(kind, bands, classes, table, x, y, regime, training)
+    np.testing.assert_allclose(res, rres.detach().numpy(), rtol=0, atol=SCORE_TOL)
+    assert_argmax(res, rres.detach().numpy())
+    for h, rh in zip(heads, rheads):
+        np.testing.assert_allclose(h, rh.detach().numpy(), rtol=0, atol=SCORE_TOL)
+    assert abs(loss - float(rloss)) < 1e-3
+    for k, rb in rbufs.items():
+        np.testing.assert_allclose(bufs[k].numpy(), rb.numpy(), rtol=1e-5, atol=1e-5)
+    for k, rg in rgrads.items():
+        g = grads[k]
+        if rg is None:
+            assert g is None or float(g.abs().max()) == 0.0, k
+            continue
+        assert g is not None, k
+        assert g.dtype == rg.dtype, k
+        err = float((g.double() - rg.double()).abs().max())
+        scale = float(rg.abs().max())
+        assert err <= 1e-5 + 1e-3 * scale, f"{k}: err {err:.3e} scale {scale:.3e}"
+
+
+def test_dead_conv1d_taps_get_exact_zero():
+    table = orc.init_params("spectral", 16, 5, 3)
+    x, y = orc.make_inputs(6, 16, 5, 3)
+    _, _, _, grads, _ = run_cuda("spectral", 16, 5, table, x, y, "R2", True)
+    for k, ks in ((1, 3), (2, 5), (3, 7)):
+        for conv in ("attention_conv1", "attention_conv2"):
+            g = grads[f"attention_{k}.{conv}.weight"]
+            dead = [t for t in range(ks) if t != ks // 2]
+            assert float(g[:, :, dead].abs().max()) == 0.0
+            assert float(g[:, :, ks // 2].abs().max()) > 0.0
+
+
+def test_running_stats_and_modes():
+    from deeptreeattention_b200 import Hang2020 as H
+    table = orc.init_params("hang2020", 20, 4, 5)
+    x, _ = orc.make_inputs(9, 20, 4, 5)
+    m = H.Hang2020(20, 4)
+    m.load_state_dict(table)
+    m = m.cuda()
+    m.train()
+    a = m(x.cuda())
+    assert int(m.spectral_network.conv1.bn1.num_batches_tracked) == 1
+    m.eval()
+    with torch.no_grad():
+        b = m(x.cuda())
+        c = m(x.cuda())
+    assert int(m.spectral_network.conv1.bn1.num_batches_tracked) == 1
+    assert torch.equal(b, c), "eval forward must be deterministic and must not touch buffers"
+    assert not torch.allclose(a, b)
+
+
+def test_cpu_input_raises():
+    from deeptreeattention_b200 import Hang2020 as H
+    m = H.Hang2020(3, 2).cuda()
+    with pytest.raises(RuntimeError):
+        m(torch.randn(2, 3, 11, 11))
+    with pytest.raises(ValueError):
+        m(torch.randn(2, 4, 11, 11).cuda())
