@@ -8,6 +8,17 @@ with the seeded parameter table from ``oracle.hang2020_oracle.init_params`` (num
 PCG64, independent of the torch RNG), run on ``make_inputs`` crops, and its outputs,
 loss, gradients and BatchNorm buffers are stored.  Large gradient tensors are stored
 as a fixed strided sample plus sum / abs-sum / l2 so the fixtures stay small.
+
+Kink screening.  The network is piecewise smooth (ReLU, max-pool argmax): a pre-activation
+that lies within fp32 rounding noise of a kink can fall on either side under a different
+summation order, which changes individual gradient elements by O(1e-2) relative -- in the
+reference itself too (CPU oneDNN vs cuDNN).  Element-wise gradient parity at 1e-3 is only
+defined away from kinks, so every case's seed is advanced until the reference's gradients are
+stable (5e-4 relative) under three random 3e-6 relative perturbations of crops and weights
+(the noise level of an fp32 evaluation with a different summation order).  The accepted seed
+is recorded in cases.json and the measured per-tensor sensitivity is stored next to each
+gradient (``grad/<name>/sens``) so tests can widen the tolerance by the reference's own
+conditioning instead of guessing.
 """
 import importlib.util
 import os
@@ -28,8 +39,8 @@ SAMPLE = 2048
 CASES = [
     ("cfg1_vanilla_b3_c2_train", "vanilla", 3, 2, 4, "uniform", "R1", True, False, 1),
     ("cfg1_vanilla_b3_c2_eval", "vanilla", 3, 2, 4, "uniform", "R1", False, True, 2),
-    ("hang_b3_c10_randn_train_R1", "hang2020", 3, 10, 20, "normal", "R1", True, False, 3),
-    ("hang_b3_c10_randn_train_R2", "hang2020", 3, 10, 20, "normal", "R2", True, True, 4),
+    ("hang_b3_c10_randn_train_R1", "hang2020", 3, 10, 6, "normal", "R1", True, False, 3),
+    ("hang_b3_c10_randn_train_R2", "hang2020", 3, 10, 5, "normal", "R2", True, True, 4),
     ("hang_b369_c50_train_R1", "hang2020", 369, 50, 8, "uniform", "R1", True, False, 5),
     ("hang_b369_c50_train_R2", "hang2020", 369, 50, 8, "uniform", "R2", True, True, 6),
     ("hang_b369_c50_eval_R2", "hang2020", 369, 50, 8, "normal", "R2", False, True, 7),
@@ -53,8 +64,46 @@ def sample_index(n):
     return np.unique(np.linspace(0, n - 1, SAMPLE).astype(np.int64))
 
 
+def kink_stable(ref, case, seed, eps=3e-6, tol=5e-4, draws=3):
+    """(stable, {name: sensitivity}): whether the reference's gradients move smoothly under
+    tiny perturbations, and by how much each tensor moved."""
+    name, kind, bands, classes, batch, dist, regime, training, perturb, _ = case
+    table = orc.init_params(kind, bands, classes, seed, perturb_bn=perturb)
+    x, y = orc.make_inputs(batch, bands, classes, seed, dist)
+    base = orc.step(kind, table, x, y, regime=regime, training=training)[3]
+    gen = torch.Generator().manual_seed(seed)
+    sens = {k: 0.0 for k, g in base.items() if g is not None}
+    stable = True
+    for _ in range(draws):
+        t2 = {k: (v * (1 + eps * torch.randn(v.shape, generator=gen, dtype=v.dtype))
+                  if (v.is_floating_point() and not orc.is_buffer(k)) else v.clone()) for k, v in table.items()}
+        x2 = x * (1 + eps * torch.randn(x.shape, generator=gen))
+        g2 = orc.step(kind, t2, x2, y, regime=regime, training=training)[3]
+        for k, g in base.items():
+            if g is None:
+                continue
+            scale = float(g.abs().max())
+            d = float((g - g2[k]).abs().max())
+            sens[k] = max(sens[k], d)
+            if d > tol * scale + 2e-6:
+                stable = False
+        if not stable:
+            break
+    return stable, sens
+
+
 def run_case(ref, case):
     name, kind, bands, classes, batch, dist, regime, training, perturb, seed = case
+    tries = 0
+    while True:
+        stable, sens = kink_stable(ref, case, seed)
+        if stable:
+            break
+        seed += 1000
+        tries += 1
+        if tries > 400:
+            raise RuntimeError(f"no kink-stable seed found for {name}")
+    case = case[:-1] + (seed,)
     table = orc.init_params(kind, bands, classes, seed, perturb_bn=perturb)
     x, y = orc.make_inputs(batch, bands, classes, seed, dist)
     cls = {"hang2020": ref.Hang2020, "spectral": ref.spectral_network,
@@ -107,7 +156,8 @@ def run_case(ref, case):
         out[f"grad/{k}/sample"] = g[idx]
         g64 = g.astype(np.float64)
         out[f"grad/{k}/stats"] = np.array([g64.sum(), np.abs(g64).sum(), np.sqrt((g64 * g64).sum())])
-    return name, out
+        out[f"grad/{k}/sens"] = np.array(sens[k], dtype=np.float64)
+    return name, out, case
 
 
 def main():
@@ -115,10 +165,10 @@ def main():
     ref = load_reference()
     meta = []
     for case in CASES:
-        name, out = run_case(ref, case)
+        name, out, case = run_case(ref, case)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         meta.append(case)
-        print(name, "loss", float(out["loss"]), "keys", len(out))
+        print(name, "seed", case[-1], "loss", float(out["loss"]), "keys", len(out), flush=True)
     with open(os.path.join(HERE, "cases.json"), "w") as f:
         import json
         json.dump({"torch": torch.__version__, "reference": "weecology/DeepTreeAttention@cae13f1",

@@ -34,10 +34,12 @@ def sample_index(n):
     return np.unique(np.linspace(0, n - 1, SAMPLE).astype(np.int64))
 
 
-def check_grads(gold, grads, rtol=1e-3, atol=2e-6, where=""):
-    """grads: {name: tensor or None}.  Weight grads: |d| <= atol + rtol*max|ref| per tensor
-    (conv biases under train-mode BN have true gradient 0 and the reference itself holds
-    ~1e-7 noise there, SURVEY Appendix C, so the absolute term matters)."""
+def check_grads(gold, grads, rtol=1e-3, atol=2e-6, where="", sens_factor=4.0):
+    """grads: {name: tensor or None}.  Weight grads: |d| <= atol + rtol*max|ref| + 4*sens per
+    tensor.  (Conv biases under train-mode BN have true gradient 0 and the reference itself
+    holds ~1e-7 noise there, SURVEY Appendix C, so the absolute term matters; ``sens`` is the
+    reference's own measured movement under 3e-6 relative input/weight perturbations, see
+    tests/golden/make_golden.py -- small for the screened, kink-stable cases.)"""
     seen = 0
     for key in gold:
         if key.startswith("gradnone/"):
@@ -53,12 +55,32 @@ def check_grads(gold, grads, rtol=1e-3, atol=2e-6, where=""):
             got = g[sample_index(g.size)]
             assert got.dtype == ref.dtype, f"{where}{name}: dtype {got.dtype} vs {ref.dtype}"
             scale = float(np.abs(ref).max())
+            sens = float(gold[f"grad/{name}/sens"]) if f"grad/{name}/sens" in gold else 0.0
             err = float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max())
-            assert err <= atol + rtol * scale, f"{where}{name}: grad err {err:.3e} scale {scale:.3e}"
+            assert err <= atol + rtol * scale + sens_factor * sens, \
+                f"{where}{name}: grad err {err:.3e} scale {scale:.3e} sens {sens:.3e}"
             stats = gold[f"grad/{name}/stats"]
             g64 = g.astype(np.float64)
             l2 = np.sqrt((g64 * g64).sum())
-            assert abs(l2 - stats[2]) <= atol * np.sqrt(g.size) + rtol * stats[2], \
+            assert abs(l2 - stats[2]) <= atol * np.sqrt(g.size) + rtol * stats[2] + sens_factor * sens * np.sqrt(g.size), \
                 f"{where}{name}: l2 {l2:.6e} vs {stats[2]:.6e}"
             seen += 1
     assert seen > 0
+
+
+def oracle_sensitivity(kind, table, x, y, regime, training, base_grads, eps=3e-6, draws=2, seed=0):
+    """Per-tensor max movement of the ORACLE's gradients under ``draws`` random ``eps``-relative
+    perturbations of crops and weights: the conditioning of the piecewise-smooth network at this
+    point (ReLU / max-pool kinks make individual elements jump when a pre-activation sits within
+    rounding noise of a kink).  Used to widen gradient tolerances by the reference's own
+    instability instead of a guessed constant."""
+    gen = torch.Generator().manual_seed(seed)
+    sens = {k: 0.0 for k, g in base_grads.items() if g is not None}
+    for _ in range(draws):
+        t2 = {k: (v * (1 + eps * torch.randn(v.shape, generator=gen, dtype=v.dtype))
+                  if (v.is_floating_point() and not orc.is_buffer(k)) else v.clone()) for k, v in table.items()}
+        x2 = x * (1 + eps * torch.randn(x.shape, generator=gen))
+        g2 = orc.step(kind, t2, x2, y, regime=regime, training=training)[3]
+        for k in sens:
+            sens[k] = max(sens[k], float((base_grads[k] - g2[k]).abs().max()))
+    return sens
