@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""Headline benchmark: hyperspectral crops/s for one Hang2020 training step (forward + weighted
+cross-entropy over the heads + backward [+ gradient all-reduce at N > 1]) on synthetic
+(B, 369, 11, 11) crops -- BASELINE.json's metric on its config
+"Full Hang2020 (spectral+spatial+3 heads), bands=369 classes=50, batch=1024 on 1xB200"
+(1024 crops PER GPU at N > 1, i.e. the 8xB200 config's 8192 global batch: weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] --steps K --warmup W  # reference algorithm on host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field's definition.
+`value`   : device-timed, crops resident in HBM.
+`e2e`     : same step through the public nn.Module API with the crops in pinned HOST memory,
+            H2D copy of every step's crops and D2H read of its loss inside the timed region.
+`roofline`: dominant kernel (by CUDA-event time inside the timed region) against the measured
+            peak of the pipe that bounds it, plus the whole step against the HBM roofline the
+            metric names (184,521 algorithmic bytes per crop at B_local = 1024).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+METRIC = "hyperspectral crops/sec (fwd+bwd, 369-band 11x11)"
+UNIT = "crops/s"
+FILTERS = (32, 64, 128)
+
+
+# ----------------------------------------------------------------------------- arithmetic
+def param_count(bands: int, classes: int) -> int:
+    """Trainable parameters of Hang2020(bands, classes) (731,836 at 369/50)."""
+    n = 1
+    cin = bands
+    for k, c in enumerate(FILTERS):
+        conv = c * cin * 9 + c + 2 * c
+        ks_spec = (3, 5, 7)[k]
+        ks_spat = (7, 5, 3)[k]
+        spec = 2 * (c * c * ks_spec + c) + classes * c + classes
+        spat = (c + 1) + 2 * (ks_spat * ks_spat + 1) + classes * 4 * c + classes
+        n += 2 * conv + spec + spat
+        cin = c
+    return n
+
+
+def algorithmic_bytes_per_crop(bands: int, classes: int, b_local: int) -> float:
+    """crop read once + label + scores written once + params read and grads
+    written once per step, amortised over the local batch."""
+    return 4.0 * bands * 121 + 8 + 4 * classes + 2.0 * 4 * param_count(bands, classes) / b_local
+
+
+def conv_flops(bands: int):
+    """Nominal FLOPs per crop of each convolution GEMM (2*Cin*Cout*9*H*W, padded taps included),
+    both branches.  Keys match the library's stage names."""
+    c1 = 2.0 * bands * 64 * 9 * 121
+    c2 = 2 * 2.0 * 32 * 64 * 9 * 121
+    c3 = 2 * 2.0 * 64 * 128 * 9 * 25
+    return {"fwd.conv1": c1, "fwd.conv2": c2, "fwd.conv3": c3,
+            "bwd.conv1_wgrad": c1, "bwd.conv2_wgrad": c2, "bwd.conv3_wgrad": c3,
+            "bwd.conv2_dgrad": c2, "bwd.conv3_dgrad": c3}
+
+
+def step_flops_per_crop(bands: int) -> float:
+    return sum(conv_flops(bands).values())
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    # B200_PROFILING.md fallback
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- workload
+def synth_batch(batch, bands, classes, seed):
+    """crops U[0,1) (the loader's per-pixel min-max scaling, src/utils.py:49),
+    labels uniform; per-rank seed."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(batch, bands, 11, 11, generator=g)
+    y = torch.randint(0, classes, (batch,), generator=g)
+    return x, y
+
+
+def loss_of(regime, joint, heads, y):
+    """R2 (default, the north star): sum of CE over the six heads (three per branch).
+    R1: the reference's TreeModel.training_step, CE(joint) (src/main.py:78)."""
+    if regime == "R1":
+        return F.cross_entropy(joint, y)
+    return sum(F.cross_entropy(h, y) for h in heads)
+
+
+def cpu_reference_rate(bands, classes, batch, regime, steps, warmup, threads):
+    """The reference's algorithm (oracle port: the same ATen CPU ops the reference's torch.nn
+    layers dispatch) for `steps` timed steps of `batch` crops on `threads` host threads."""
+    from oracle import hang2020_oracle as orc
+    torch.set_num_threads(threads)
+    m = orc.OracleModule("hang2020", bands, classes, seed=0).train()
+    x, y = synth_batch(batch, bands, classes, 0)
+    times = []
+    for i in range(warmup + steps):
+        for p in m.parameters():
+            p.grad = None
+        t0 = time.perf_counter()
+        joint = m(x)
+        loss = loss_of(regime, joint, m.heads, y)
+        loss.backward()
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+    total = sum(times)
+    return batch * steps / total, total / steps
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU path (kind "port": /root/reference is Python
+    and cannot travel to the GPU box; the oracle restates it over the same ATen kernels and is
+    pinned to the reference's outputs by tests/golden)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = cores
+    batch = args.batch
+    # bound the run: calibrate on a small sample, shrink the per-step sample until the whole
+    # --steps/--warmup run fits in ~150 s
+    rate0, _ = cpu_reference_rate(args.bands, args.classes, 64, args.regime, 1, 1, threads)
+    budget = 150.0
+    while batch > 64 and (args.steps + args.warmup) * batch / rate0 > budget:
+        batch //= 2
+    rate, sec = cpu_reference_rate(args.bands, args.classes, batch, args.regime, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Hang2020(bands={args.bands}, classes={args.classes}) fwd+CE({args.regime})+bwd, "
+                               f"{batch} crops per step on host cores", "regime": args.regime},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {batch} crops after {args.warmup} warm-up, torch {torch.__version__} "
+                                   f"CPU ATen (oneDNN) on {threads} threads of {cores} cores"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- this repo's arm
+def run_b200(args):
+    import torch.distributed as dist
+    from deeptreeattention_b200 import Hang2020 as H
+    from deeptreeattention_b200 import _capi, distributed as D
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
+    rank, world, local = D.init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    B, bands, classes = args.batch, args.bands, args.classes
+
+    torch.manual_seed(0)                       # same replica on every rank (DDP semantics)
+    model = H.Hang2020(bands, classes).to(dev).train()
+    sync = D.GradSync(model)
+    x_host, y_host = synth_batch(B, bands, classes, seed=rank)
+    x_pin = [x_host.pin_memory(), x_host.clone().pin_memory()]
+    y_dev = y_host.to(dev)
+    x_dev = x_host.to(dev)
+    params = list(model.parameters())
+
+    def train_step(xd):
+        for p in params:
+            p.grad = None
+        joint = model(xd)
+        loss = loss_of(args.regime, joint, model.head_scores, y_dev)
+        loss.backward()
+        sync.sync()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        train_step(x_dev)
+    torch.cuda.synchronize()
+    _capi.set_option(local, "profile", 1)
+    _capi.profile_read(local, reset=True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches = 0
+    barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        train_step(x_dev)
+        launches += _capi.get_option(local, "launches")      # backward's count (host counter)
+    e1.record()
+    torch.cuda.synchronize(); barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clock_rec = clocks.stop() if rank == 0 else None
+    stages = _capi.profile_read(local, reset=True)
+    _capi.set_option(local, "profile", 0)
+    # forward's launch count: one extra forward outside the timed region
+    with torch.no_grad():
+        model(x_dev)
+    fwd_launches = _capi.get_option(local, "launches")
+    torch.cuda.synchronize()
+    launches += fwd_launches * args.steps
+    ms_step = ms_total / args.steps
+    value = world * B / (ms_step * 1e-3)
+
+    # ---- end to end through the public API, crops in pinned host memory ---------------------
+    copy_stream = torch.cuda.Stream(dev)
+    x_buf = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        s = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[s])
+            x_buf[s].copy_(x_pin[s], non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in (0, 1):
+            consumed[s].record(torch.cuda.current_stream())
+        prefetch(0)
+        last = 0.0
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1)                      # next step's crops cross PCIe under this step's math
+            torch.cuda.current_stream().wait_event(ready[i & 1])
+            loss = train_step(x_buf[i & 1])
+            consumed[i & 1].record(torch.cuda.current_stream())
+            last = loss.item()                       # D2H read of the step's result
+        return last
+
+    e2e_loop(3)
+    torch.cuda.synchronize(); barrier()
+    t0 = time.perf_counter()
+    e2e_loop(args.steps)
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * B * args.steps / t_e2e
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline ---------------------------------------------------------------------------
+    peaks = measured_peaks()
+    flops = conv_flops(bands)
+    stage_ms = {k: v[0] / args.steps for k, v in stages.items()}             # ms per step (all launches of the stage)
+    launch_ms = {k: v[0] / max(v[1], 1) for k, v in stages.items()}          # ms per launch
+    dominant = max(stage_ms, key=stage_ms.get) if stage_ms else None
+    bytes_per_crop = algorithmic_bytes_per_crop(bands, classes, B)
+    hbm_roof = peaks["hbm_gbs"] * 1e9 / bytes_per_crop
+    roof = {"bound": "tensor", "kernel": dominant, "unit": "TFLOP/s", "peak": peaks["bf16_tflops_sustained"],
+            "peak_source": f"{peaks['source']} bf16 dense, sustained (kernel timed inside a long step)", "traffic": None}
+    if dominant is not None:
+        d_ms = launch_ms[dominant]
+        d_flops = flops.get(dominant, 0.0) * B
+        roof["launch_ms"] = d_ms
+        roof["share_of_step"] = stage_ms[dominant] / ms_step
+        roof["achieved"] = d_flops / (d_ms * 1e-3) / 1e12 if d_ms > 0 else None
+        roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+        roof["flops_per_launch"] = d_flops
+    roof["step_hbm"] = {"bound": "hbm", "achieved": (value / world) * bytes_per_crop / 1e9, "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": (value / world) / hbm_roof, "bytes_per_crop": bytes_per_crop,
+                        "roofline_crops_per_s_per_gpu": hbm_roof}
+    roof["step_tensor"] = {"achieved": (value / world) * step_flops_per_crop(bands) / 1e12, "peak": peaks["bf16_tflops_sustained"],
+                           "unit": "TFLOP/s", "frac": (value / world) * step_flops_per_crop(bands) / 1e12 / peaks["bf16_tflops_sustained"],
+                           "flops_per_crop": step_flops_per_crop(bands)}
+    roof["stages_ms_per_step"] = {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}
+    traffic_file = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            t = json.load(f)
+        if t.get("kernel") == dominant:
+            roof["traffic"] = t.get("dram_bytes_per_launch")
+
+    # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        rate0, _ = cpu_reference_rate(bands, classes, 64, args.regime, 1, 1, cores)
+        cb = B
+        while cb > 64 and 3 * cb / rate0 > 25.0:
+            cb //= 2
+        rate, _ = cpu_reference_rate(bands, classes, cb, args.regime, 2, 1, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"2 timed steps x {cb} crops (1 warm-up) of the same workload, oracle port on torch {torch.__version__} CPU ATen, {cores} threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"Hang2020(bands={bands}, classes={classes}) fwd+CE({args.regime})+bwd"
+                               + ("+grad all-reduce" if world > 1 else "") + f", {B} crops per GPU per step",
+                   "regime": args.regime, "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}", "l2": f"crops per step = {B * bands * 484 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
+                   if B * bands * 484 > 126e6 else "flush: none (inputs smaller than L2)"},
+        "roofline": roof, "cpu_baseline": cpu, "clocks": clock_rec,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_dev.numel() * 4, "d2h_bytes_per_step": 4,
+                "how": "pinned host crops -> double-buffered H2D on a copy stream -> model(x) -> CE -> backward -> loss.item()"},
+        "gpu_launches": launches,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="crops per GPU per step")
+    ap.add_argument("--bands", type=int, default=369)
+    ap.add_argument("--classes", type=int, default=50)
+    ap.add_argument("--regime", default="R2", choices=["R1", "R2"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

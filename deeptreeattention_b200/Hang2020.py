@@ -74,6 +74,19 @@ class _NetSpec:
     def __init__(self, kind, bands, classes):
         self.kind, self.bands, self.classes = kind, bands, classes
         self.n_heads = {_capi.NET_HANG2020: 6, _capi.NET_SPECTRAL: 3, _capi.NET_SPATIAL: 3, _capi.NET_VANILLA: 1}[kind]
+        # set by the last backward: the flat fp32 gradient buffer every float parameter's
+        # .grad is a view of, and alpha's fp64 gradient (distributed.GradSync reduces these)
+        self.flat_grad = None
+        self.alpha_grad = None
+        self._table_key = None
+        self._table = None
+
+    def table_for(self, ptr_of: Dict[str, int]):
+        """C parameter table for these device pointers (rebuilt only when a pointer moved)."""
+        key = tuple(ptr_of.values())
+        if key != self._table_key:
+            self._table, self._table_key = _fill_tensors(self.kind, ptr_of), key
+        return self._table
 
 
 def _stream_ptr(device) -> int:
@@ -93,7 +106,7 @@ class _FusedNetFunction(torch.autograd.Function):
         sizes = _capi.query_sizes(spec.kind, B, spec.bands, spec.classes, training)
         ptr_of = {n: p.data_ptr() for n, p in zip(names, params)}
         ptr_of.update({n: b.data_ptr() for n, b in buffers.items()})
-        table = _fill_tensors(spec.kind, ptr_of)
+        table = spec.table_for(ptr_of)
         with torch.cuda.device(dev):
             scores = [torch.empty((B, spec.classes), dtype=torch.float32, device=dev) for _ in range(spec.n_heads)]
             joint = torch.empty((B, spec.classes), dtype=torch.float32, device=dev) if spec.kind == _capi.NET_HANG2020 else None
@@ -128,7 +141,8 @@ class _FusedNetFunction(torch.autograd.Function):
         if djoint is not None:
             djoint = djoint.contiguous().float()
         ptr_of = {n: p.data_ptr() for n, p in zip(ctx.names, params)}
-        table = _fill_tensors(spec.kind, ptr_of)
+        ptr_of.update({n: b.data_ptr() for n, b in ctx.buffers.items()})
+        table = spec.table_for(ptr_of)
         with torch.cuda.device(dev):
             # every float gradient lives in ONE flat buffer (a single all-reduce covers it)
             numels = [p.numel() if p.dtype == torch.float32 else 0 for p in params]
@@ -148,6 +162,7 @@ class _FusedNetFunction(torch.autograd.Function):
                                   djoint.data_ptr() if djoint is not None else None, C.byref(gtable), None,
                                   work.data_ptr(), _stream_ptr(dev))
         _capi.check(handle, rc, "dta_backward")
+        spec.flat_grad, spec.alpha_grad = flat, (galpha if djoint is not None else None)
         out = []
         for name, g, need in zip(ctx.names, grads, ctx.needs_input_grad[5:]):
             if not need:
@@ -178,19 +193,36 @@ class _FusedNet(Module):
         if x.dim() != 4 or x.shape[1] != self._bands or x.shape[2] != 11 or x.shape[3] != 11:
             raise ValueError(f"expected crops of shape (B, {self._bands}, 11, 11), got {tuple(x.shape)}")
         x = x.contiguous()
-        sd = self.state_dict(keep_vars=True)
-        names, params, buffers = [], [], {}
-        for k, v in sd.items():
-            if isinstance(v, nn.Parameter):
-                names.append(k)
-                params.append(v)
-            else:
-                buffers[k] = v
-        for p in params:
-            if p.device != x.device:
-                raise RuntimeError(f"parameter on {p.device} but crops on {x.device}")
-        spec = _NetSpec(self._net_kind, self._bands, self._classes)
+        cache = self.__dict__.get("_fused_cache")
+        if cache is not None and (next(self.buffers()) is not cache[4] or next(self.parameters()) is not cache[1][0]):
+            cache = None                                # a sub-module was moved/replaced on its own
+        if cache is None:
+            names, params, buffers = [], [], {}
+            for k, v in self.state_dict(keep_vars=True).items():
+                if isinstance(v, nn.Parameter):
+                    names.append(k)
+                    params.append(v)
+                else:
+                    buffers[k] = v
+            cache = (names, params, buffers, _NetSpec(self._net_kind, self._bands, self._classes), next(self.buffers()))
+            self.__dict__["_fused_cache"] = cache
+        names, params, buffers, spec = cache[:4]
+        if params[0].device != x.device:
+            raise RuntimeError(f"parameter on {params[0].device} but crops on {x.device}")
         return _FusedNetFunction.apply(x, spec, self.training, names, buffers, *params)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_fused_cache", None)      # .cuda()/.to() replace buffers (and maybe parameters)
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.__dict__.pop("_fused_cache", None)
+        return super().load_state_dict(*args, **kwargs)
+
+    def fused_spec(self):
+        """Spec of the last fused call (holds the flat gradient buffer after a backward)."""
+        cache = self.__dict__.get("_fused_cache")
+        return cache[3] if cache is not None else None
 
 
 # ------------------------------------------------------------------- reference API surface

@@ -49,8 +49,12 @@ class Sizes(C.Structure):
                 ("n_heads", C.c_int32)]
 
 
+class StageTime(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("total_ms", C.c_double), ("calls", C.c_int64)]
+
+
 EXPORTS = ["dta_abi_version", "dta_create", "dta_destroy", "dta_last_error", "dta_set_option", "dta_get_option",
-           "dta_query_sizes", "dta_forward", "dta_backward"]
+           "dta_profile_read", "dta_query_sizes", "dta_forward", "dta_backward"]
 
 
 def sources():
@@ -114,6 +118,8 @@ def lib():
         L.dta_set_option.restype = C.c_int
         L.dta_get_option.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
         L.dta_get_option.restype = C.c_int
+        L.dta_profile_read.argtypes = [C.c_void_p, C.POINTER(StageTime), C.c_int, C.POINTER(C.c_int), C.c_int]
+        L.dta_profile_read.restype = C.c_int
         L.dta_query_sizes.argtypes = [C.POINTER(Shape), C.POINTER(Sizes)]
         L.dta_query_sizes.restype = C.c_int
         L.dta_forward.argtypes = [C.c_void_p, C.POINTER(Shape), C.c_void_p, C.POINTER(Tensors),
@@ -177,3 +183,12 @@ def get_option(device_index: int, key: str) -> int:
     if rc != DTA_OK:
         raise ValueError(f"unknown option {key}")
     return v.value
+
+
+def profile_read(device_index: int, reset: bool = True):
+    """{stage: (total_ms, calls)} recorded since the last reset (option "profile" must be 1)."""
+    ctx = context(device_index)
+    rows = (StageTime * 64)()
+    n = C.c_int()
+    check(ctx, lib().dta_profile_read(ctx, rows, 64, C.byref(n), int(reset)), "dta_profile_read")
+    return {rows[i].name.decode(): (rows[i].total_ms, rows[i].calls) for i in range(min(n.value, 64))}

@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "dta_attention.cuh"
 #include "dta_common.cuh"
@@ -11,11 +12,23 @@
 
 using namespace dta;
 
+// Stage timing (option "profile"): CUDA events recorded on the caller's stream around each
+// named stage; dta_profile_read() folds them into per-stage totals.
+struct ProfSpan {
+  int stage;
+  cudaEvent_t t0, t1;
+};
 struct dta_ctx {
   int device = 0;
   int sm_count = 0;
   int conv_impl = 0;
   long long launches = 0;
+  int profile = 0;
+  std::vector<std::string> stage_names;
+  std::vector<double> stage_ms;
+  std::vector<long long> stage_calls;
+  std::vector<ProfSpan> spans;
+  std::vector<cudaEvent_t> free_events;
   std::string err;
 };
 
@@ -152,6 +165,57 @@ BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
   W.wd[2] = c.take((size_t)d.nb * 128 * 9 * 64);
   W.bytes = c.off;
   return W;
+}
+
+int stage_index(dta_ctx* ctx, const char* name) {
+  for (size_t i = 0; i < ctx->stage_names.size(); ++i)
+    if (ctx->stage_names[i] == name) return (int)i;
+  ctx->stage_names.push_back(name);
+  ctx->stage_ms.push_back(0.0);
+  ctx->stage_calls.push_back(0);
+  return (int)ctx->stage_names.size() - 1;
+}
+cudaEvent_t take_event(dta_ctx* ctx) {
+  if (!ctx->free_events.empty()) {
+    cudaEvent_t e = ctx->free_events.back();
+    ctx->free_events.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+// RAII bracket around the launches of one stage.
+struct StageScope {
+  dta_ctx* ctx;
+  cudaStream_t st;
+  ProfSpan span{};
+  bool on;
+  StageScope(dta_ctx* c, const char* name, cudaStream_t s) : ctx(c), st(s), on(c->profile != 0) {
+    if (!on) return;
+    span.stage = stage_index(c, name);
+    span.t0 = take_event(c);
+    span.t1 = take_event(c);
+    cudaEventRecord(span.t0, st);
+  }
+  ~StageScope() {
+    if (!on) return;
+    cudaEventRecord(span.t1, st);
+    ctx->spans.push_back(span);
+  }
+};
+void fold_spans(dta_ctx* ctx) {
+  for (ProfSpan& sp : ctx->spans) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(sp.t1) == cudaSuccess && cudaEventElapsedTime(&ms, sp.t0, sp.t1) == cudaSuccess) {
+      ctx->stage_ms[sp.stage] += ms;
+      ctx->stage_calls[sp.stage] += 1;
+    }
+    ctx->free_events.push_back(sp.t0);
+    ctx->free_events.push_back(sp.t1);
+  }
+  ctx->spans.clear();
+  cudaGetLastError();
 }
 
 int fail(dta_ctx* ctx, int code, const std::string& msg) {
@@ -308,7 +372,29 @@ int dta_create(dta_ctx** out, int device) {
   return DTA_OK;
 }
 
-void dta_destroy(dta_ctx* ctx) { delete ctx; }
+void dta_destroy(dta_ctx* ctx) {
+  if (!ctx) return;
+  fold_spans(ctx);
+  for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+  delete ctx;
+}
+
+int dta_profile_read(dta_ctx* ctx, dta_stage_time* out, int capacity, int* count, int reset) {
+  if (!ctx || !count) return DTA_ERR_INVALID_ARG;
+  fold_spans(ctx);
+  const int n = (int)ctx->stage_names.size();
+  *count = n;
+  for (int i = 0; i < n && i < capacity && out; ++i) {
+    memset(out[i].name, 0, sizeof(out[i].name));
+    strncpy(out[i].name, ctx->stage_names[i].c_str(), sizeof(out[i].name) - 1);
+    out[i].total_ms = ctx->stage_ms[i];
+    out[i].calls = ctx->stage_calls[i];
+  }
+  if (reset) {
+    for (int i = 0; i < n; ++i) { ctx->stage_ms[i] = 0.0; ctx->stage_calls[i] = 0; }
+  }
+  return DTA_OK;
+}
 
 const char* dta_last_error(const dta_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -319,6 +405,10 @@ int dta_set_option(dta_ctx* ctx, const char* key, int64_t value) {
     ctx->conv_impl = (int)value;
     return DTA_OK;
   }
+  if (!strcmp(key, "profile")) {
+    ctx->profile = value != 0;
+    return DTA_OK;
+  }
   return fail(ctx, DTA_ERR_INVALID_ARG, std::string("unknown option ") + key);
 }
 
@@ -326,6 +416,7 @@ int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value) {
   if (!ctx || !key || !value) return DTA_ERR_INVALID_ARG;
   if (!strcmp(key, "conv_impl")) { *value = ctx->conv_impl; return DTA_OK; }
   if (!strcmp(key, "launches")) { *value = ctx->launches; return DTA_OK; }
+  if (!strcmp(key, "profile")) { *value = ctx->profile; return DTA_OK; }
   if (!strcmp(key, "sm_count")) { *value = ctx->sm_count; return DTA_OK; }
   return DTA_ERR_INVALID_ARG;
 }
@@ -363,6 +454,8 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   FwdWork W = layout_fwd(*shape, d, workspace);
 
   // 1. pack parameters into kernel-friendly tables (a few MB, once per step)
+  StageScope* pack_scope = new StageScope(ctx, "fwd.pack_params", st);
+  struct ScopeDrop { StageScope*& p; ~ScopeDrop() { delete p; p = nullptr; } } pack_drop{pack_scope};
   for (int k = 0; k < 3; ++k) {
     Ptr2 w{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}};
     const int cin = k == 0 ? bands : kC[k - 1];
@@ -380,10 +473,12 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     }
   }
 
+  delete pack_scope; pack_scope = nullptr;
   cudaError_t e;
   int nblk = 0;
   // 2. block 1: conv1 over the crops (both branches share the read of x)
   {
+    StageScope sc(ctx, "fwd.conv1", st);
     ConvSrc src = src_raw(x, bands, kHW);
     Ptr2 bias{{params->branch[0].conv[0].conv_b, nb > 1 ? params->branch[1].conv[0].conv_b : nullptr}};
     float* stats = shape->training ? W.stats : nullptr;
@@ -393,6 +488,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     ctx->launches++;
   }
   auto bn_finalize = [&](int k, int nblk_k) -> int {
+    StageScope sc(ctx, "fwd.bn_finalize", st);
     const int ctot = nb * kC[k];
     bn_fwd_finalize_kernel<<<(ctot * 32 + 255) / 256, 256, 0, st>>>(W.stats, nblk_k, ctot, (double)B * kHWpre[k], bn_params(params, d, k),
                                                                     shape->training, L.bn_mean[k], L.bn_istd[k], L.bn_scale[k], L.bn_shift[k]);
@@ -407,6 +503,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   };
   if ((rc = bn_finalize(0, nblk)) != DTA_OK) return rc;
   if (!vanilla) {
+    StageScope sc(ctx, "fwd.attn1", st);
     auto kern = attn_fwd_kernel<32, 11, false>;
     const size_t sm = attn_fwd_smem<32, 11, false>();
     allow_smem(kern, sm);
@@ -415,6 +512,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   }
   // 3. block 2
   {
+    StageScope sc(ctx, "fwd.conv2", st);
     ConvSrc src = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
     Ptr2 bias{{params->branch[0].conv[1].conv_b, nb > 1 ? params->branch[1].conv[1].conv_b : nullptr}};
     e = launch_fprop<11, 1, 8, 8, 64, 16>(src, L.wp[1], bias, 64, L.z[1], nb * 64, shape->training ? W.stats : nullptr, B, nb, st, &nblk);
@@ -423,6 +521,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   }
   if ((rc = bn_finalize(1, nblk)) != DTA_OK) return rc;
   if (!vanilla) {
+    StageScope sc(ctx, "fwd.attn2", st);
     auto kern = attn_fwd_kernel<64, 11, true>;
     const size_t sm = attn_fwd_smem<64, 11, true>();
     allow_smem(kern, sm);
@@ -431,6 +530,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   }
   // 4. block 3
   {
+    StageScope sc(ctx, "fwd.conv3", st);
     ConvSrc src = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
     Ptr2 bias{{params->branch[0].conv[2].conv_b, nb > 1 ? params->branch[1].conv[2].conv_b : nullptr}};
     e = launch_fprop<5, 4, 4, 8, 128, 8>(src, L.wp[2], bias, 128, L.z[2], nb * 128, shape->training ? W.stats : nullptr, B, nb, st, &nblk);
@@ -439,6 +539,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   }
   if ((rc = bn_finalize(2, nblk)) != DTA_OK) return rc;
   {
+    StageScope sc(ctx, "fwd.attn3", st);
     auto kern = attn_fwd_kernel<128, 5, true>;
     const size_t sm = attn_fwd_smem<128, 5, true>();
     allow_smem(kern, sm);
@@ -447,6 +548,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   }
   // 5. alpha blend + copies of the last-head scores for dalpha
   if (shape->net_kind == DTA_NET_HANG2020) {
+    StageScope sc(ctx, "fwd.joint", st);
     const size_t n = (size_t)B * classes;
     joint_fwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(scores[2], scores[5], params->alpha, joint, n);
     DTA_CHECK_LAUNCH(ctx, "joint_fwd");
@@ -484,6 +586,8 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   // upstream gradients per head (the alpha blend folds djoint into the two last heads)
   const float* dS[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int h = 0; h < d.n_heads; ++h) dS[h] = dscores[h];
+  StageScope* pre_scope = new StageScope(ctx, "bwd.prologue", st);
+  struct ScopeDrop { StageScope*& p; ~ScopeDrop() { delete p; p = nullptr; } } pre_drop{pre_scope};
   if (hang && djoint) {
     joint_bwd_kernel<<<(int)((nsc + 255) / 256), 256, 0, st>>>(dscores[2], dscores[5], djoint, params->alpha, W.dS[2], W.dS[5], nsc);
     DTA_CHECK_LAUNCH(ctx, "joint_bwd");
@@ -529,6 +633,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     }
   }
 
+  delete pre_scope; pre_scope = nullptr;
   auto bn_grads = [&](int k) {
     BnGrads g{};
     for (int b = 0; b < nb; ++b) {
@@ -538,6 +643,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     return g;
   };
   auto bn_bwd = [&](int k) -> int {
+    StageScope sc(ctx, "bwd.bn_finalize", st);
     const int ctot = nb * kC[k];
     bn_bwd_finalize_kernel<<<(ctot * 32 + 255) / 256, 256, 0, st>>>(W.bnrows, B, nb, kC[k], (double)B * kHWpre[k], bn_params(params, d, k),
                                                                     L.bn_mean[k], L.bn_istd[k], shape->training, bn_grads(k), W.k0[k], W.k1[k], W.k2[k]);
@@ -546,6 +652,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   };
   // small parameter gradients of one attention block + head, reduced over the batch
   auto attn_param_grads = [&](int k) -> int {
+    StageScope sc(ctx, "bwd.small_param_grads", st);
     const int C = kC[k], ld = kProwLd[k];
     for (int g = 0; g < nb; ++g) {
       const dta_branch& gb = grads->branch[g];
@@ -599,6 +706,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     return p;
   };
   auto reduce_w = [&](int k, int cin) -> int {
+    StageScope sc(ctx, "bwd.wgrad_reduce", st);
     MutPtr2 dw{{grads->branch[0].conv[k].conv_w, nb > 1 ? grads->branch[1].conv[k].conv_w : nullptr}};
     const size_t per_branch = (size_t)kC[k] * cin * 9;
     wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W.wpart, sp.n[k], 1, per_branch * nb, dw, per_branch);
@@ -611,18 +719,20 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     auto kern = attn_bwd_kernel<128, 5, true>;
     const size_t sm = attn_bwd_smem<128, 5, true>(classes);
     allow_smem(kern, sm);
+    StageScope* asc = new StageScope(ctx, "bwd.attn3", st);
     kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], L.bn_mean[2], L.bn_istd[2], attn_prm(2), classes, L.att[2], L.feat[2],
                                               ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow);
+    delete asc;
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<3>");
     if ((rc = attn_param_grads(2)) != DTA_OK) return rc;
     if ((rc = bn_bwd(2)) != DTA_OK) return rc;
     ConvSrc dz = src_dz(W.da[2], L.z[2], 128, nb * 128, 25, W.k0[2], W.k1[2], W.k2[2]);
     ConvSrc in = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
-    e = launch_wgrad<5, 32, 128, 8>(in, dz, W.wpart, B, sp.n[2], sp.per[2], nb, st);
+    { StageScope sc(ctx, "bwd.conv3_wgrad", st); e = launch_wgrad<5, 32, 128, 8>(in, dz, W.wpart, B, sp.n[2], sp.per[2], nb, st); }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 wgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
     if ((rc = reduce_w(2, 64)) != DTA_OK) return rc;
-    e = launch_fprop<5, 4, 4, 8, 64, 8>(dz, W.wd[2], Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, nullptr, B, nb, st, nullptr);
+    { StageScope sc(ctx, "bwd.conv3_dgrad", st); e = launch_fprop<5, 4, 4, 8, 64, 8>(dz, W.wd[2], Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, nullptr, B, nb, st, nullptr); }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 dgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
   }
@@ -631,18 +741,20 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     auto kern = attn_bwd_kernel<64, 11, true>;
     const size_t sm = attn_bwd_smem<64, 11, true>(classes);
     allow_smem(kern, sm);
+    StageScope* asc = new StageScope(ctx, "bwd.attn2", st);
     kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], L.bn_mean[1], L.bn_istd[1], attn_prm(1), classes, L.att[1], L.feat[1],
                                               ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow);
+    delete asc;
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<2>");
     if ((rc = attn_param_grads(1)) != DTA_OK) return rc;
     if ((rc = bn_bwd(1)) != DTA_OK) return rc;
     ConvSrc dz = src_dz(W.da[1], L.z[1], 64, nb * 64, 121, W.k0[1], W.k1[1], W.k2[1]);
     ConvSrc in = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
-    e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[1], sp.per[1], nb, st);
+    { StageScope sc(ctx, "bwd.conv2_wgrad", st); e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[1], sp.per[1], nb, st); }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 wgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
     if ((rc = reduce_w(1, 32)) != DTA_OK) return rc;
-    e = launch_fprop<11, 1, 8, 4, 32, 16>(dz, W.wd[1], Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, nullptr, B, nb, st, nullptr);
+    { StageScope sc(ctx, "bwd.conv2_dgrad", st); e = launch_fprop<11, 1, 8, 4, 32, 16>(dz, W.wd[1], Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, nullptr, B, nb, st, nullptr); }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 dgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
   }
@@ -651,15 +763,20 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     auto kern = attn_bwd_kernel<32, 11, false>;
     const size_t sm = attn_bwd_smem<32, 11, false>(classes);
     allow_smem(kern, sm);
+    StageScope* asc = new StageScope(ctx, "bwd.attn1", st);
     kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], L.bn_mean[0], L.bn_istd[0], attn_prm(0), classes, L.att[0], L.feat[0],
                                               ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow);
+    delete asc;
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<1>");
     if ((rc = attn_param_grads(0)) != DTA_OK) return rc;
     if ((rc = bn_bwd(0)) != DTA_OK) return rc;
     ConvSrc dz = src_dz(W.da[0], L.z[0], nb * 32, nb * 32, 121, W.k0[0], W.k1[0], W.k2[0]);
     ConvSrc in = src_raw(x, bands, kHW);
-    if (nb == 2) e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
-    else e = launch_wgrad<11, 32, 32, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
+    {
+      StageScope sc(ctx, "bwd.conv1_wgrad", st);
+      if (nb == 2) e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
+      else e = launch_wgrad<11, 32, 32, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
+    }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv1 wgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
     if ((rc = reduce_w(0, bands)) != DTA_OK) return rc;

@@ -117,9 +117,23 @@ const char* dta_last_error(const dta_ctx* ctx); /* ctx may be NULL: last create 
 
 /* Tuning / debugging knobs.  key "conv_impl": 0 = fp32 CUDA-core direct convolution,
  * 1 = tcgen05 split-bf16 implicit GEMM (default where implemented).
- * key "launches": read-only counter of kernels launched by the last forward/backward. */
+ * key "launches": read-only counter of kernels launched by the last forward/backward.
+ * key "profile": 1 = record per-stage CUDA-event timings (see dta_profile_read). */
 int dta_set_option(dta_ctx* ctx, const char* key, int64_t value);
 int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value);
+
+/* Stage timing.  With option "profile" = 1 every forward/backward brackets its stages
+ * (conv1 fprop, attention block k, conv1 wgrad, ...) with CUDA events on the caller's
+ * stream.  dta_profile_read synchronises the recorded events, folds them into per-stage
+ * totals and copies up to `capacity` rows to `out` (`*count` = rows available); `reset`
+ * != 0 clears the totals afterwards.  Used by bench.py for the roofline of the dominant
+ * kernel; costs two event records per stage, nothing when the option is 0. */
+typedef struct dta_stage_time {
+  char name[40];
+  double total_ms;
+  int64_t calls;
+} dta_stage_time;
+int dta_profile_read(dta_ctx* ctx, dta_stage_time* out, int capacity, int* count, int reset);
 
 /* Pure host arithmetic: buffer sizes for a shape (no GPU needed). */
 int dta_query_sizes(const dta_shape* shape, dta_sizes* out);
