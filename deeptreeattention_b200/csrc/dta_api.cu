@@ -8,6 +8,7 @@
 #include "dta_attention.cuh"
 #include "dta_common.cuh"
 #include "dta_conv_simt.cuh"
+#include "dta_conv_tc.cuh"
 #include "dta_misc.cuh"
 
 using namespace dta;
@@ -21,7 +22,7 @@ struct ProfSpan {
 struct dta_ctx {
   int device = 0;
   int sm_count = 0;
-  int conv_impl = 0;
+  int conv_impl = 1;   // 1: tcgen05 split-bf16 implicit GEMM where built (conv1 forward + weight gradient), 0: fp32 SIMT
   long long launches = 0;
   int profile = 0;
   std::vector<std::string> stage_names;
@@ -73,7 +74,36 @@ struct Carver {
   }
 };
 
+// Geometry of the tensor-core path for conv1 (plane side 11, merged 64 output channels).
+struct TcGeom {
+  size_t rows;        // rows of a packed position-stream buffer
+  int nstage;         // forward K stages (16 input channels each)
+  int nchunk;         // 8-channel chunks allocated for the packed crops (multiple of 6 and 2)
+  int ntiles;         // forward tiles of 512 positions
+  int nkstage;        // wgrad K stages (128 positions each)
+  int nslices;        // wgrad input-channel slices (48 channels each)
+  int nsplit, stages_per_split;
+};
+TcGeom tc_geom(int B, int bands, int sm_count) {
+  TcGeom g{};
+  constexpr int TILE = TcFprop<11, 64>::TILE;
+  g.rows = tc_rows(B, Stream<11>::PC, TILE);
+  g.nstage = (bands + 15) / 16;
+  g.nchunk = (2 * g.nstage + 5) / 6 * 6;
+  g.ntiles = (int)((g.rows - 2 * kTcGuard) / TILE);
+  g.nkstage = (int)((g.rows - 2 * kTcGuard) / TcWgrad::KROWS);
+  g.nslices = g.nchunk / 6;
+  int want = sm_count / g.nslices;
+  if (want < 1) want = 1;
+  if (want > g.nkstage) want = g.nkstage;
+  g.stages_per_split = (g.nkstage + want - 1) / want;
+  g.nsplit = (g.nkstage + g.stages_per_split - 1) / g.stages_per_split;
+  return g;
+}
+constexpr int kTcSmCount = 148;   // workspace sizing (dta_query_sizes has no device); launches use the real count, capped to this
+
 struct SavedLayout {
+  __nv_bfloat16* xp;   // split-bf16 position stream of the crops (conv1 forward and weight gradient)
   float* z[3];
   float* bn_mean[3]; float* bn_istd[3]; float* bn_scale[3]; float* bn_shift[3];
   float* att[3];
@@ -102,18 +132,24 @@ SavedLayout layout_saved(const dta_shape& s, const NetDesc& d, void* base) {
   for (int g = 0; g < 2; ++g)
     for (int k = 0; k < 3; ++k)
       for (int q = 0; q < 4; ++q) L.spec_pack[g][k][q] = c.take((size_t)kC[k] * kC[k]);
+  {
+    const TcGeom g = tc_geom(s.batch, s.bands, kTcSmCount);
+    L.xp = reinterpret_cast<__nv_bfloat16*>(c.take((size_t)2 * g.nchunk * g.rows * 4));   // 16 B per (half, chunk, row)
+  }
   L.bytes = c.off;
   return L;
 }
 
 struct FwdWork {
   float* stats;
+  __nv_bfloat16* wpf;   // packed forward weights of conv1 for the tensor-core path
   size_t bytes;
 };
 FwdWork layout_fwd(const dta_shape& s, const NetDesc& d, void* base) {
   FwdWork W{};
   Carver c(base);
   W.stats = c.take((size_t)s.batch * d.nb * 128 * 2);
+  W.wpf = reinterpret_cast<__nv_bfloat16*>(c.take((size_t)tc_geom(s.batch, s.bands, kTcSmCount).nstage * (TcFprop<11, 64>::W_BYTES / 4)));
   W.bytes = c.off;
   return W;
 }
@@ -141,6 +177,7 @@ struct BwdWork {
   float* prow;
   float* wpart;
   float* wd[3];
+  __nv_bfloat16* dzp;   // split-bf16 position stream of conv1's output gradient (tensor-core wgrad)
   size_t bytes;
 };
 BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
@@ -159,7 +196,11 @@ BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
   const size_t wp2 = (size_t)sp.n[1] * d.nb * 64 * 32 * 9, wp3 = (size_t)sp.n[2] * d.nb * 128 * 64 * 9;
   if (wp2 > wp) wp = wp2;
   if (wp3 > wp) wp = wp3;
+  const TcGeom tg = tc_geom(s.batch, s.bands, kTcSmCount);
+  const size_t wp_tc = (size_t)(tg.nsplit + 1) * 64 * s.bands * 9;
+  if (wp_tc > wp) wp = wp_tc;
   W.wpart = c.take(wp);
+  W.dzp = reinterpret_cast<__nv_bfloat16*>(c.take((size_t)2 * 8 * tg.rows * 4));
   W.wd[0] = c.take((size_t)d.nb * 32 * 9 * s.bands);
   W.wd[1] = c.take((size_t)d.nb * 64 * 9 * 32);
   W.wd[2] = c.take((size_t)d.nb * 128 * 9 * 64);
@@ -401,7 +442,7 @@ const char* dta_last_error(const dta_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int dta_set_option(dta_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return DTA_ERR_INVALID_ARG;
   if (!strcmp(key, "conv_impl")) {
-    if (value != 0) return fail(ctx, DTA_ERR_UNSUPPORTED, "conv_impl: only 0 (fp32 direct) is built in this version");
+    if (value != 0 && value != 1) return fail(ctx, DTA_ERR_INVALID_ARG, "conv_impl must be 0 (fp32 direct) or 1 (tcgen05 split-bf16)");
     ctx->conv_impl = (int)value;
     return DTA_OK;
   }
@@ -477,7 +518,35 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   cudaError_t e;
   int nblk = 0;
   // 2. block 1: conv1 over the crops (both branches share the read of x)
-  {
+  if (ctx->conv_impl == 1) {
+    // tensor-core path: pack crops + weights, implicit GEMM, batch statistics of z
+    const TcGeom g = tc_geom(B, bands, kTcSmCount);
+    Ptr2 bias{{params->branch[0].conv[0].conv_b, nb > 1 ? params->branch[1].conv[0].conv_b : nullptr}};
+    Ptr2 w{{params->branch[0].conv[0].conv_w, nb > 1 ? params->branch[1].conv[0].conv_w : nullptr}};
+    {
+      StageScope sc(ctx, "fwd.conv1_pack", st);
+      tc_pack_stream_kernel<11><<<ctx->sm_count * 8, 256, 0, st>>>(src_raw(x, bands, kHW), 1, B, g.nchunk, g.rows, L.xp);
+      DTA_CHECK_LAUNCH(ctx, "tc_pack_stream(x)");
+      tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, st>>>(w, nb, 32, bands, g.nstage, W.wpf);
+      DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
+    }
+    {
+      StageScope sc(ctx, "fwd.conv1", st);
+      using Cfg = TcFprop<11, 64>;
+      auto kern = tc_conv_fprop_kernel<11, 64>;
+      if ((e = allow_smem(kern, Cfg::SMEM_BYTES)) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv1 fprop attr: ") + cudaGetErrorString(e));
+      const int grid = g.ntiles < ctx->sm_count ? g.ntiles : ctx->sm_count;
+      kern<<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(L.xp, g.rows, g.nchunk, W.wpf, g.nstage, bias, 32, L.z[0], nb * 32, B, g.ntiles);
+      DTA_CHECK_LAUNCH(ctx, "tc_conv_fprop");
+    }
+    if (shape->training) {
+      StageScope sc(ctx, "fwd.conv1_stats", st);
+      const int per = 8;
+      nblk = (B + per - 1) / per;
+      bn_partial_stats_kernel<<<dim3(nblk, (nb * 32 + 7) / 8), 256, 0, st>>>(L.z[0], B, nb * 32, kHW, per, W.stats);
+      DTA_CHECK_LAUNCH(ctx, "bn_partial_stats");
+    }
+  } else {
     StageScope sc(ctx, "fwd.conv1", st);
     ConvSrc src = src_raw(x, bands, kHW);
     Ptr2 bias{{params->branch[0].conv[0].conv_b, nb > 1 ? params->branch[1].conv[0].conv_b : nullptr}};
@@ -705,11 +774,11 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     for (int g = 0; g < nb; ++g) p.p[g] = head_ds(g, k);
     return p;
   };
-  auto reduce_w = [&](int k, int cin) -> int {
+  auto reduce_w = [&](int k, int cin, int nsplit) -> int {
     StageScope sc(ctx, "bwd.wgrad_reduce", st);
     MutPtr2 dw{{grads->branch[0].conv[k].conv_w, nb > 1 ? grads->branch[1].conv[k].conv_w : nullptr}};
     const size_t per_branch = (size_t)kC[k] * cin * 9;
-    wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W.wpart, sp.n[k], 1, per_branch * nb, dw, per_branch);
+    wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W.wpart, nsplit, 1, per_branch * nb, dw, per_branch);
     DTA_CHECK_LAUNCH(ctx, "wgrad_reduce");
     return DTA_OK;
   };
@@ -731,7 +800,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     { StageScope sc(ctx, "bwd.conv3_wgrad", st); e = launch_wgrad<5, 32, 128, 8>(in, dz, W.wpart, B, sp.n[2], sp.per[2], nb, st); }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 wgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
-    if ((rc = reduce_w(2, 64)) != DTA_OK) return rc;
+    if ((rc = reduce_w(2, 64, sp.n[2])) != DTA_OK) return rc;
     { StageScope sc(ctx, "bwd.conv3_dgrad", st); e = launch_fprop<5, 4, 4, 8, 64, 8>(dz, W.wd[2], Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, nullptr, B, nb, st, nullptr); }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 dgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
@@ -753,7 +822,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     { StageScope sc(ctx, "bwd.conv2_wgrad", st); e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[1], sp.per[1], nb, st); }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 wgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
-    if ((rc = reduce_w(1, 32)) != DTA_OK) return rc;
+    if ((rc = reduce_w(1, 32, sp.n[1])) != DTA_OK) return rc;
     { StageScope sc(ctx, "bwd.conv2_dgrad", st); e = launch_fprop<11, 1, 8, 4, 32, 16>(dz, W.wd[1], Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, nullptr, B, nb, st, nullptr); }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 dgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
@@ -772,14 +841,29 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     if ((rc = bn_bwd(0)) != DTA_OK) return rc;
     ConvSrc dz = src_dz(W.da[0], L.z[0], nb * 32, nb * 32, 121, W.k0[0], W.k1[0], W.k2[0]);
     ConvSrc in = src_raw(x, bands, kHW);
-    {
+    int conv1_nsplit = sp.n[0];
+    if (ctx->conv_impl == 1) {
+      const TcGeom g = tc_geom(B, bands, kTcSmCount);
+      {
+        StageScope sc(ctx, "bwd.conv1_pack", st);
+        tc_pack_stream_kernel<11><<<ctx->sm_count * 8, 256, 0, st>>>(dz, 1, B, 8, g.rows, W.dzp);
+        DTA_CHECK_LAUNCH(ctx, "tc_pack_stream(dz)");
+      }
+      StageScope sc(ctx, "bwd.conv1_wgrad", st);
+      auto kern = tc_conv_wgrad_kernel<11>;
+      if ((e = allow_smem(kern, TcWgrad::SMEM_BYTES)) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv1 wgrad attr: ") + cudaGetErrorString(e));
+      kern<<<dim3(g.nslices, g.nsplit), kTcThreads, TcWgrad::SMEM_BYTES, st>>>(W.dzp, L.xp, g.rows, g.nchunk, bands, nb * 32, g.nkstage,
+                                                                             g.stages_per_split, W.wpart);
+      e = cudaGetLastError();
+      conv1_nsplit = g.nsplit;
+    } else {
       StageScope sc(ctx, "bwd.conv1_wgrad", st);
       if (nb == 2) e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
       else e = launch_wgrad<11, 32, 32, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
     }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv1 wgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
-    if ((rc = reduce_w(0, bands)) != DTA_OK) return rc;
+    if ((rc = reduce_w(0, bands, conv1_nsplit)) != DTA_OK) return rc;
     if (dx) return fail(ctx, DTA_ERR_UNSUPPORTED, "gradient of the crops (dx) is not built yet; the reference feeds requires_grad=False inputs");
   }
   e = cudaGetLastError();

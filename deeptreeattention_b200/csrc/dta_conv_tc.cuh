@@ -1,0 +1,444 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM 3x3 "same" convolution for sm_100a: forward and
+// weight gradient, fp32-faithful through split-bf16 operands (v = hi + lo, products
+// hi*hi + hi*lo + lo*hi [+ lo*lo], fp32 accumulation in tensor memory).  conv_impl = 1.
+// Reference semantics: nn.Conv2d(k=3, padding="same"), Hang2020.py:18.
+//
+// Data layout ("position stream").  A crop plane of side S is laid out with one zero pad row
+// above it and one zero pad column to its right: pitch PT = S+1, PC = (S+1)*PT positions per
+// crop (S=11: 12 x 12 = 144).  The next crop's pad row is this crop's bottom padding, the pad
+// column is the right padding of row y and the left padding of row y+1.  Crops follow each other,
+// so the whole batch is ONE stream of positions q = b*PC + (y+1)*PT + x and every 3x3 tap is a
+// constant shift s = dy*PT + dx of that stream.  Operands are pre-packed (dta_pack_* kernels) as
+//     buf[half][chunk][row = GUARD + q][8 x bf16]     half: 0 = hi, 1 = lo;  chunk = 8 channels
+// so (a) a tile's rows are contiguous in global memory -> plain 1-D bulk copies (TMA engine, no
+// tensor map), (b) in shared memory the same bytes are a canonical no-swizzle UMMA operand, K-major
+// (forward: row = M) or MN-major (wgrad: row = K), and (c) a tap is `start address += s * 16 B`
+// (dta_tc.cuh; verified on hardware by tools/tc_probe.cu).
+#pragma once
+#include "dta_common.cuh"
+#include "dta_tc.cuh"
+
+namespace dta {
+
+constexpr int kTcGuard = 16;       // zero rows before the first / after the last crop (>= PT + 1)
+constexpr int kTcThreads = 192;    // warp 0: bulk-copy producer, warp 1: MMA issuer, warps 2-5: epilogue
+
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" : : : "memory"); }
+
+// Geometry of the position stream for plane side S.
+template <int S>
+struct Stream {
+  static constexpr int PT = S + 1;          // pitch
+  static constexpr int PC = (S + 1) * PT;   // positions per crop
+};
+
+// Rows of a packed operand buffer for `B` crops read in tiles of `tile` positions.
+inline size_t tc_rows(int B, int pc, int tile) {
+  const size_t n = (size_t)B * pc;
+  return (n + tile - 1) / tile * tile + 2 * kTcGuard;
+}
+
+// =======================================================================================
+// Packing kernels (HBM-bound elementwise; one thread = 8 channels x 1 stream position)
+// =======================================================================================
+// Crops / activations -> split-bf16 position stream.  src is produced by conv_src_load, so the
+// same kernel packs raw crops (SRC_RAW), gated activations (SRC_ACT) and BatchNorm-backward
+// gradients (SRC_DZ).  Channels >= cin_total, pad positions and guard rows are written as zeros.
+//   dst[half][chunk][rows][8],  chunk = channel / 8 over the concatenated groups
+template <int S>
+__global__ void tc_pack_stream_kernel(ConvSrc src, int G, int B, int nchunk, size_t rows, __nv_bfloat16* __restrict__ dst) {
+  using St = Stream<S>;
+  const size_t total = rows * nchunk;
+  const int ctot = G * src.cin;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int chunk = (int)(i / rows);
+    const size_t row = i - (size_t)chunk * rows;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    const long long q = (long long)row - kTcGuard;
+    if (q >= 0 && q < (long long)B * St::PC) {
+      const int b = (int)(q / St::PC);
+      const int r = (int)(q - (long long)b * St::PC);
+      const int yy = r / St::PT, xx = r - yy * St::PT;
+      if (yy >= 1 && xx < S) {
+        const int p = (yy - 1) * S + xx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int ch = chunk * 8 + j;
+          if (ch < ctot) {
+            const int g = ch / src.cin;
+            v[j] = conv_src_load<S>(src, b, g, G, ch - g * src.cin, p);
+          }
+        }
+      }
+    }
+    uint4 hi, lo;
+    tc::split2(v[0], v[1], hi.x, lo.x);
+    tc::split2(v[2], v[3], hi.y, lo.y);
+    tc::split2(v[4], v[5], hi.z, lo.z);
+    tc::split2(v[6], v[7], hi.w, lo.w);
+    reinterpret_cast<uint4*>(dst)[i] = hi;
+    reinterpret_cast<uint4*>(dst)[total + i] = lo;
+  }
+}
+
+// Forward weights -> per 16-input-channel stage: [stage][tap 9][kchunk 2][row 2*NCO: hi co | lo co][8 ci].
+// w.p[br] = conv_layer.weight (cout_b, cin, 3, 3); merged output channel = br*cout_b + co (conv1 reads the
+// same crops for both branches); rows of absent channels are zero.
+template <int NCO>
+__global__ void tc_pack_w_fprop_kernel(Ptr2 w, int nb, int cout_b, int cin, int nstage, __nv_bfloat16* __restrict__ dst) {
+  const size_t total = (size_t)nstage * 9 * 2 * (2 * NCO) * 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    size_t r = i;
+    const int j = (int)(r % 8); r /= 8;
+    const int row = (int)(r % (2 * NCO)); r /= (2 * NCO);
+    const int kc = (int)(r % 2); r /= 2;
+    const int tap = (int)(r % 9); r /= 9;
+    const int stage = (int)r;
+    const int half = row / NCO, co = row - half * NCO;
+    const int ci = stage * 16 + kc * 8 + j;
+    float v = 0.f;
+    const int br = co / cout_b;
+    if (br < nb && ci < cin) v = __ldg(w.p[br] + ((size_t)(co - br * cout_b) * cin + ci) * 9 + tap);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    dst[i] = half == 0 ? h : __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// =======================================================================================
+// Forward: z[b][co][p] = bias[co] + sum_{ci,tap} x[b][ci][p + tap] * W[co][ci][tap]
+//   GEMM view: M = stream positions (tiles of 4 x 128), N = NCO output channels, K = ci (16 per stage) x 9 taps.
+//   Per (subtile, tap, 16 ci): MMA1  A_hi x [W_hi ; W_lo]  (N = 2*NCO)  -> cols [0,NCO) += hi*hi, [NCO,2NCO) += hi*lo
+//                              MMA2  A_lo x  W_hi          (N = NCO)    -> cols [0,NCO) += lo*hi
+//   Epilogue: z = cols[0,NCO) + cols[NCO,2NCO) + bias.
+// =======================================================================================
+template <int S, int NCO>
+struct TcFprop {
+  using St = Stream<S>;
+  static constexpr int SUB = 512 / (2 * NCO);            // 128-position subtiles per tile (all 512 TMEM columns)
+  static constexpr int TILE = SUB * 128;
+  static constexpr int AROWS = TILE + 2 * kTcGuard;      // rows staged per chunk
+  static constexpr int A_BYTES = 2 * 2 * AROWS * 16;     // [half][kchunk][AROWS][16 B]
+  static constexpr int W_BYTES = 9 * 2 * (2 * NCO) * 16; // [tap][kchunk][2*NCO][16 B]
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr int NSTAGE = (222 * 1024) / STAGE_BYTES >= 4 ? 4 : (222 * 1024) / STAGE_BYTES;
+  static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 1024;
+  static_assert(NSTAGE >= 2, "stage too large");
+  static_assert(kTcGuard >= St::PT + 1, "guard must cover the largest tap shift");
+};
+
+template <int S, int NCO>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]*/, size_t rows, int nchunk,
+                     const __nv_bfloat16* __restrict__ wp /*[nstage][W_BYTES]*/, int nstage, Ptr2 bias, int bias_split,
+                     float* __restrict__ z /*[B][cout][S*S]*/, int cout, int B, int ntiles) {
+  using Cfg = TcFprop<S, NCO>;
+  using St = Stream<S>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t full_bar[4], empty_bar[4], tmem_full, tmem_empty;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < Cfg::NSTAGE; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    tc::mbar_init(&tmem_full, 1);
+    tc::mbar_init(&tmem_empty, 4);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const size_t half_stride = (size_t)nchunk * rows * 8;   // elements between the hi and lo planes
+
+  if (warp == 0) {
+    // ---------------- producer: bulk copies global -> shared ----------------
+    if (elect_one_sync()) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t row0 = (size_t)tile * Cfg::TILE;       // first staged row (= GUARD + q0 - GUARD)
+        for (int ks = 0; ks < nstage; ++ks, ++it) {
+          const int st = it % Cfg::NSTAGE;
+          const uint32_t ph = (it / Cfg::NSTAGE) & 1;
+          tc::mbar_wait(&empty_bar[st], ph ^ 1);
+          unsigned char* sa = smem + (size_t)st * Cfg::STAGE_BYTES;
+          tc::mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc)
+              tc::bulk_g2s(sa + (size_t)(h * 2 + kc) * Cfg::AROWS * 16,
+                           xp + h * half_stride + ((size_t)(ks * 2 + kc) * rows + row0) * 8, Cfg::AROWS * 16, &full_bar[st]);
+          tc::bulk_g2s(sa + Cfg::A_BYTES, wp + (size_t)ks * (Cfg::W_BYTES / 2), Cfg::W_BYTES, &full_bar[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer (warp-uniform loop, one elected lane issues) ----------------
+    const uint32_t leader = elect_one_sync();
+    constexpr uint32_t idesc1 = tc::make_idesc_bf16(128, 2 * NCO, 0, 0);
+    constexpr uint32_t idesc2 = tc::make_idesc_bf16(128, NCO, 0, 0);
+    uint32_t it = 0, tile_it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+      tc::mbar_wait(&tmem_empty, (tile_it & 1) ^ 1);
+      tc::fence_after_sync();
+      for (int ks = 0; ks < nstage; ++ks, ++it) {
+        const int st = it % Cfg::NSTAGE;
+        const uint32_t ph = (it / Cfg::NSTAGE) & 1;
+        tc::mbar_wait(&full_bar[st], ph);
+        tc::fence_after_sync();
+        // descriptors of row 0; the address field is the low 14 bits, so "+ rows" below moves the start
+        const uint32_t sa = tc::smem_u32(smem + (size_t)st * Cfg::STAGE_BYTES);
+        const uint64_t a_d = tc::sdesc_kmajor(sa, Cfg::AROWS);                              // A_hi plane
+        const uint64_t b_d = tc::sdesc_kmajor(sa + Cfg::A_BYTES, 2 * NCO);
+        const uint32_t a_lo32 = (uint32_t)a_d, a_hi32 = (uint32_t)(a_d >> 32);
+        const uint32_t al_lo32 = a_lo32 + 2 * Cfg::AROWS;                                   // A_lo plane
+        const uint32_t b_lo32 = (uint32_t)b_d, b_hi32 = (uint32_t)(b_d >> 32);
+#pragma unroll
+        for (int s = 0; s < Cfg::SUB; ++s) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int shift = kTcGuard + s * 128 + (t / 3 - 1) * St::PT + (t % 3 - 1);   // rows == 16-byte units
+            const uint32_t boff = t * (2 * (2 * NCO));                                    // 16-byte units per tap
+            if (leader) {
+              tc::mma_bf16(tmem + s * (2 * NCO), desc_from(a_lo32 + shift, a_hi32), desc_from(b_lo32 + boff, b_hi32), idesc1,
+                           (ks | t) ? 1u : 0u);
+              tc::mma_bf16(tmem + s * (2 * NCO), desc_from(al_lo32 + shift, a_hi32), desc_from(b_lo32 + boff, b_hi32), idesc2, 1u);
+            }
+          }
+        }
+        __syncwarp();
+        if (leader) tc::mma_commit(&empty_bar[st]);
+      }
+      if (leader) tc::mma_commit(&tmem_full);
+      __syncwarp();
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> z (NCHW fp32) ----------------
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    uint32_t tile_it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+      tc::mbar_wait(&tmem_full, tile_it & 1);
+      tc::fence_after_sync();
+#pragma unroll 1
+      for (int s = 0; s < Cfg::SUB; ++s) {
+        const long long q = (long long)tile * Cfg::TILE + s * 128 + quad * 32 + lane;
+        const int b = (int)(q / St::PC);
+        const int r = (int)(q - (long long)b * St::PC);
+        const int yy = r / St::PT, xx = r - yy * St::PT;
+        const bool valid = b < B && yy >= 1 && xx < S;
+        float* zrow = z + ((size_t)b * cout) * (S * S) + (yy - 1) * S + xx;
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + s * (2 * NCO);
+#pragma unroll 1
+        for (int c0 = 0; c0 < NCO; c0 += 16) {
+          float v0[16], v1[16];
+          tc::tmem_ld16(taddr + c0, v0);
+          tc::tmem_ld16(taddr + NCO + c0, v1);
+          tc::tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int ch = c0 + j;
+              if (ch < cout) {
+                const float bv = __ldg(bias.p[ch / bias_split] + (ch % bias_split));
+                zrow[(size_t)ch * (S * S)] = v0[j] + v1[j] + bv;
+              }
+            }
+          }
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+// =======================================================================================
+// Weight gradient: dW[co][ci][tap] = sum_q dz[q][co] * x[q + s_tap][ci]   (q over the whole stream)
+//   GEMM view per tap: M = 2*64 rows [dz_hi co ; dz_lo co] (A, MN-major, shifted by -s_tap),
+//   N = 48 input channels of this CTA's slice (B, MN-major), K = stream positions (128 per stage).
+//   Two MMAs per (tap, 16 positions): B = x_hi and B = x_lo -> rows co hold dz_hi*x, rows 64+co dz_lo*x
+//   (all four partial products); 9 taps x 48 columns = 432 TMEM columns.  Split-K over the stream:
+//   part[split][co][ci][tap], summed in fixed order by wgrad_reduce_kernel.
+// =======================================================================================
+struct TcWgrad {
+  static constexpr int NCI = 48;                          // input channels per CTA slice (6 chunks)
+  static constexpr int KROWS = 128;                       // stream positions per stage
+  static constexpr int AROWS = KROWS + 2 * kTcGuard;      // dz rows staged per chunk (taps reach +-13)
+  static constexpr int A_BYTES = 16 * AROWS * 16;         // [hi 8 | lo 8 chunks][AROWS][16 B]
+  static constexpr int B_BYTES = 2 * 6 * KROWS * 16;      // [half][6 chunks][KROWS][16 B]
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int NSTAGE = 3;
+  static constexpr int RED_BYTES = 64 * NCI * 4;          // lo-half partials for the epilogue
+  static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + RED_BYTES + 1024;
+};
+
+template <int S>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][8][rows][8]*/, const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]*/,
+                     size_t rows, int nchunk, int cin, int cout, int nkstage_total, int stages_per_split,
+                     float* __restrict__ part /*[nsplit][cout][cin][9]*/) {
+  using Cfg = TcWgrad;
+  using St = Stream<S>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  float* s_red = reinterpret_cast<float*>(smem + (size_t)Cfg::NSTAGE * Cfg::STAGE_BYTES);
+  __shared__ uint64_t full_bar[Cfg::NSTAGE], empty_bar[Cfg::NSTAGE], tmem_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int lane = tid & 31;
+  const int slice = blockIdx.x, split = blockIdx.y;
+  const int ks_begin = split * stages_per_split;
+  const int ks_end = min(nkstage_total, ks_begin + stages_per_split);
+  const int nks = max(0, ks_end - ks_begin);
+
+  if (tid == 0) {
+    for (int i = 0; i < Cfg::NSTAGE; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    tc::mbar_init(&tmem_full, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      const size_t dz_half = (size_t)8 * rows * 8, x_half = (size_t)nchunk * rows * 8;
+      for (int i = 0; i < nks; ++i) {
+        const int st = i % Cfg::NSTAGE;
+        const uint32_t ph = (i / Cfg::NSTAGE) & 1;
+        tc::mbar_wait(&empty_bar[st], ph ^ 1);
+        unsigned char* sa = smem + (size_t)st * Cfg::STAGE_BYTES;
+        unsigned char* sb = sa + Cfg::A_BYTES;
+        const size_t k0 = (size_t)(ks_begin + i) * Cfg::KROWS;     // first stream position of the stage
+        tc::mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
+        // dz rows [GUARD + k0 - GUARD, +AROWS)
+        for (int c = 0; c < 16; ++c)
+          tc::bulk_g2s(sa + (size_t)c * Cfg::AROWS * 16, dzp + (c / 8) * dz_half + ((size_t)(c % 8) * rows + k0) * 8, Cfg::AROWS * 16,
+                       &full_bar[st]);
+        // x rows [GUARD + k0, +KROWS) of this slice's 6 chunks
+        for (int h = 0; h < 2; ++h)
+          for (int c = 0; c < 6; ++c)
+            tc::bulk_g2s(sb + (size_t)(h * 6 + c) * Cfg::KROWS * 16,
+                         xp + h * x_half + ((size_t)(slice * 6 + c) * rows + kTcGuard + k0) * 8, Cfg::KROWS * 16, &full_bar[st]);
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t leader = elect_one_sync();
+    constexpr uint32_t idesc = tc::make_idesc_bf16(128, Cfg::NCI, 1, 1);
+    for (int i = 0; i < nks; ++i) {
+      const int st = i % Cfg::NSTAGE;
+      const uint32_t ph = (i / Cfg::NSTAGE) & 1;
+      tc::mbar_wait(&full_bar[st], ph);
+      tc::fence_after_sync();
+      const uint32_t sa = tc::smem_u32(smem + (size_t)st * Cfg::STAGE_BYTES);
+      const uint64_t a_d = tc::sdesc_mnmajor(sa, Cfg::AROWS);
+      const uint64_t b_d = tc::sdesc_mnmajor(sa + Cfg::A_BYTES, Cfg::KROWS);
+      const uint32_t a_lo32 = (uint32_t)a_d, a_hi32 = (uint32_t)(a_d >> 32);
+      const uint32_t b_lo32 = (uint32_t)b_d, b_hi32 = (uint32_t)(b_d >> 32);
+#pragma unroll
+      for (int kk = 0; kk < Cfg::KROWS / 16; ++kk) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int arow = kTcGuard + kk * 16 - ((t / 3 - 1) * St::PT + (t % 3 - 1));   // dz row for x row kk*16
+          if (leader) {
+            tc::mma_bf16(tmem + t * Cfg::NCI, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + kk * 16, b_hi32), idesc,
+                         (i | kk) ? 1u : 0u);
+            tc::mma_bf16(tmem + t * Cfg::NCI, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + 6 * Cfg::KROWS + kk * 16, b_hi32),
+                         idesc, 1u);
+          }
+        }
+      }
+      __syncwarp();
+      if (leader) tc::mma_commit(&empty_bar[st]);
+    }
+    if (leader) tc::mma_commit(&tmem_full);
+    __syncwarp();
+  } else {
+    // epilogue: rows co (< 64) + rows 64 + co -> part[split][co][ci][tap]
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;          // TMEM lane = A row
+    if (nks > 0) {
+      tc::mbar_wait(&tmem_full, 0);
+      tc::fence_after_sync();
+    }
+    for (int t = 0; t < 9; ++t) {
+      float v[Cfg::NCI];
+      if (nks > 0) {
+#pragma unroll
+        for (int c0 = 0; c0 < Cfg::NCI; c0 += 16) tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + t * Cfg::NCI + c0, v + c0);
+        tc::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < Cfg::NCI; ++j) v[j] = 0.f;
+      }
+      if (row >= 64) {
+#pragma unroll
+        for (int j = 0; j < Cfg::NCI; ++j) s_red[(row - 64) * Cfg::NCI + j] = v[j];
+      }
+      epi_bar_sync();
+      if (row < 64 && row < cout) {
+        float* dst = part + (((size_t)split * cout + row) * cin + (size_t)slice * Cfg::NCI) * 9 + t;
+#pragma unroll
+        for (int j = 0; j < Cfg::NCI; ++j)
+          if (slice * Cfg::NCI + j < cin) dst[(size_t)j * 9] = v[j] + s_red[row * Cfg::NCI + j];
+      }
+      epi_bar_sync();
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+// Per-channel sum / sum of squares of z[b][c][hw] over groups of crops (BatchNorm batch statistics
+// when the producing kernel has no statistics epilogue).  grid = (crop groups, ceil(C / 8)), 256 threads:
+// one warp per channel.  out[group][C][2].
+__global__ void bn_partial_stats_kernel(const float* __restrict__ z, int B, int C, int hw, int crops_per_group,
+                                        float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.y * 8 + warp;
+  if (c >= C) return;
+  const int b0 = blockIdx.x * crops_per_group, b1 = min(B, b0 + crops_per_group);
+  float s = 0.f, q = 0.f;
+  for (int b = b0; b < b1; ++b) {
+    const float* p = z + ((size_t)b * C + c) * hw;
+    for (int i = lane; i < hw; i += 32) {
+      const float v = __ldg(p + i);
+      s += v;
+      q = fmaf(v, v, q);
+    }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) {
+    out[((size_t)blockIdx.x * C + c) * 2 + 0] = s;
+    out[((size_t)blockIdx.x * C + c) * 2 + 1] = q;
+  }
+}
+
+}  // namespace dta

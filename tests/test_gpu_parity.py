@@ -83,7 +83,11 @@ def test_cuda_matches_oracle(kind, bands, classes, batch, regime, training):
     x, y = orc.make_inputs(batch, bands, classes, seed, "uniform" if batch % 2 == 0 else "normal")
     rloss, rres, rheads, rgrads, rbufs = orc.step(kind, table, x, y, regime=regime, training=training)
     rres = rres[-1] if isinstance(rres, list) else rres
-    sens = gu.oracle_sensitivity(kind, table, x, y, regime, training, rgrads, draws=4)
+    # The tensor-core convolutions carry split-bf16 rounding: conv outputs are within ~1e-5 (relative) of fp32
+    # instead of ~2e-6, which flips the odd ReLU / max-pool decision whose pre-activation sits that close to its
+    # kink.  The gradient tolerance therefore includes how far the ORACLE's own gradient moves under a
+    # perturbation of that size (eps).
+    sens = gu.oracle_sensitivity(kind, table, x, y, regime, training, rgrads, eps=1e-5, draws=4)
     loss, res, heads, grads, bufs = run_cuda(kind, bands, classes, table, x, y, regime, training)
     np.testing.assert_allclose(res, rres.detach().numpy(), rtol=0, atol=SCORE_TOL)
     assert_argmax(res, rres.detach().numpy())
