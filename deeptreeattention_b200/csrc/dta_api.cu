@@ -74,36 +74,48 @@ struct Carver {
   }
 };
 
-// Geometry of the tensor-core path for conv1 (plane side 11, merged 64 output channels).
-struct TcGeom {
-  size_t rows;        // rows of a packed position-stream buffer
-  int nstage;         // forward K stages (16 input channels each)
-  int nchunk;         // 8-channel chunks allocated for the packed crops (multiple of 6 and 2)
-  int ntiles;         // forward tiles of 512 positions
-  int nkstage;        // wgrad K stages (128 positions each)
-  int nslices;        // wgrad input-channel slices (48 channels each)
-  int nsplit, stages_per_split;
-};
-TcGeom tc_geom(int B, int bands, int sm_count) {
-  TcGeom g{};
-  constexpr int TILE = TcFprop<11, 64>::TILE;
-  g.rows = tc_rows(B, Stream<11>::PC, TILE);
-  g.nstage = (bands + 15) / 16;
-  g.nchunk = (2 * g.nstage + 5) / 6 * 6;
-  g.ntiles = (int)((g.rows - 2 * kTcGuard) / TILE);
-  g.nkstage = (int)((g.rows - 2 * kTcGuard) / TcWgrad::KROWS);
-  g.nslices = g.nchunk / 6;
-  int want = sm_count / g.nslices;
+// Tensor-core path geometry.  Two position streams: side 11 (conv1, conv2 and their gradients) and
+// side 5 (conv3).  Buffers are padded so that every kernel's tile size divides the stream length.
+using WgradCfg1 = TcWgrad<48, 128, true>;    // conv1: merged 64 output channels (hi/lo stacked), 48-channel slices of the crops
+using WgradCfg2 = TcWgrad<32, 128, true>;    // conv2: 64 output channels per branch, 32 input channels
+using WgradCfg3 = TcWgrad<32, 64, false>;    // conv3: 128 output channels per branch, 2 slices of 32 input channels
+constexpr int kTcSmCount = 148;              // split-K factors are sized for the B200's 148 SMs (dta_query_sizes has no device)
+
+struct TcSplit { int nkstage, nslices, nsplit, per; };
+TcSplit tc_split(size_t rows, int krows, int cin_g, int nci, int G) {
+  TcSplit t{};
+  t.nkstage = (int)((rows - 2 * kTcGuard) / krows);
+  t.nslices = (cin_g + nci - 1) / nci;
+  int want = kTcSmCount / (t.nslices * G);
   if (want < 1) want = 1;
-  if (want > g.nkstage) want = g.nkstage;
-  g.stages_per_split = (g.nkstage + want - 1) / want;
-  g.nsplit = (g.nkstage + g.stages_per_split - 1) / g.stages_per_split;
+  if (want > t.nkstage) want = t.nkstage;
+  t.per = (t.nkstage + want - 1) / want;
+  t.nsplit = (t.nkstage + t.per - 1) / t.per;
+  return t;
+}
+struct TcGeom {
+  size_t rows11, rows5;   // rows of the packed streams
+  int nstage1;            // conv1 forward K stages (16 input channels each)
+  int nchunk1;            // 8-channel chunks allocated for the packed crops (multiple of 6 and 2)
+  TcSplit w1, w2, w3;     // weight-gradient decompositions
+};
+TcGeom tc_geom(int B, int bands, int nb) {
+  TcGeom g{};
+  g.rows11 = tc_rows(B, Stream<11>::PC, 1024);
+  g.rows5 = tc_rows(B, Stream<5>::PC, 512);
+  g.nstage1 = (bands + 15) / 16;
+  g.nchunk1 = (2 * g.nstage1 + 5) / 6 * 6;
+  g.w1 = tc_split(g.rows11, WgradCfg1::KROWS, g.nchunk1 * 8, WgradCfg1::NCI, 1);
+  g.w2 = tc_split(g.rows11, WgradCfg2::KROWS, 32, WgradCfg2::NCI, nb);
+  g.w3 = tc_split(g.rows5, WgradCfg3::KROWS, 64, WgradCfg3::NCI, nb);
   return g;
 }
-constexpr int kTcSmCount = 148;   // workspace sizing (dta_query_sizes has no device); launches use the real count, capped to this
+inline __nv_bfloat16* take_bf16(Carver& c, size_t n16) { return reinterpret_cast<__nv_bfloat16*>(c.take(n16 * 4)); }
 
 struct SavedLayout {
-  __nv_bfloat16* xp;   // split-bf16 position stream of the crops (conv1 forward and weight gradient)
+  __nv_bfloat16* xp;    // split-bf16 position stream of the crops (conv1 forward and weight gradient)
+  __nv_bfloat16* a1p;   // ... of the gated block-1 activations (conv2 forward and weight gradient)
+  __nv_bfloat16* a2p;   // ... of the gated, pooled block-2 activations (conv3)
   float* z[3];
   float* bn_mean[3]; float* bn_istd[3]; float* bn_scale[3]; float* bn_shift[3];
   float* att[3];
@@ -133,8 +145,10 @@ SavedLayout layout_saved(const dta_shape& s, const NetDesc& d, void* base) {
     for (int k = 0; k < 3; ++k)
       for (int q = 0; q < 4; ++q) L.spec_pack[g][k][q] = c.take((size_t)kC[k] * kC[k]);
   {
-    const TcGeom g = tc_geom(s.batch, s.bands, kTcSmCount);
-    L.xp = reinterpret_cast<__nv_bfloat16*>(c.take((size_t)2 * g.nchunk * g.rows * 4));   // 16 B per (half, chunk, row)
+    const TcGeom g = tc_geom(s.batch, s.bands, d.nb);
+    L.xp = take_bf16(c, (size_t)2 * g.nchunk1 * g.rows11);   // 16 B per (half, chunk, row)
+    L.a1p = take_bf16(c, (size_t)2 * d.nb * 4 * g.rows11);
+    L.a2p = take_bf16(c, (size_t)2 * d.nb * 8 * g.rows5);
   }
   L.bytes = c.off;
   return L;
@@ -142,14 +156,16 @@ SavedLayout layout_saved(const dta_shape& s, const NetDesc& d, void* base) {
 
 struct FwdWork {
   float* stats;
-  __nv_bfloat16* wpf;   // packed forward weights of conv1 for the tensor-core path
+  __nv_bfloat16* wpf[3];   // packed forward weights of conv1..3 for the tensor-core path
   size_t bytes;
 };
 FwdWork layout_fwd(const dta_shape& s, const NetDesc& d, void* base) {
   FwdWork W{};
   Carver c(base);
   W.stats = c.take((size_t)s.batch * d.nb * 128 * 2);
-  W.wpf = reinterpret_cast<__nv_bfloat16*>(c.take((size_t)tc_geom(s.batch, s.bands, kTcSmCount).nstage * (TcFprop<11, 64>::W_BYTES / 4)));
+  W.wpf[0] = take_bf16(c, (size_t)tc_geom(s.batch, s.bands, d.nb).nstage1 * (TcFprop<11, 64>::W_BYTES / 16));
+  W.wpf[1] = take_bf16(c, (size_t)d.nb * 2 * (TcFprop<11, 64>::W_BYTES / 16));
+  W.wpf[2] = take_bf16(c, (size_t)d.nb * 4 * (TcFprop<5, 128>::W_BYTES / 16));
   W.bytes = c.off;
   return W;
 }
@@ -174,10 +190,11 @@ struct BwdWork {
   float* dout[2];   // gradient wrt gated output of block 1, 2
   float* bnrows;
   float* k0[3]; float* k1[3]; float* k2[3];
-  float* prow;
+  float* prow[3];   // per-crop partial parameter gradients of each attention block
   float* wpart;
   float* wd[3];
-  __nv_bfloat16* dzp;   // split-bf16 position stream of conv1's output gradient (tensor-core wgrad)
+  __nv_bfloat16* dzp;      // split-bf16 position stream of the current block's conv-output gradient
+  __nv_bfloat16* wdp[2];   // packed input-gradient weights of conv2, conv3 (tensor-core path)
   size_t bytes;
 };
 BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
@@ -190,17 +207,24 @@ BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
   W.dout[1] = c.take(B * d.nb * 64 * 25);
   W.bnrows = c.take(B * d.nb * 256);
   for (int k = 0; k < 3; ++k) { W.k0[k] = c.take(d.nb * kC[k]); W.k1[k] = c.take(d.nb * kC[k]); W.k2[k] = c.take(d.nb * kC[k]); }
-  W.prow = c.take(B * d.nb * 256);
+  for (int k = 0; k < 3; ++k) W.prow[k] = c.take(B * d.nb * 256);
   const Splits sp = wgrad_splits(s.batch);
   size_t wp = (size_t)sp.n[0] * d.nb * 32 * s.bands * 9;
   const size_t wp2 = (size_t)sp.n[1] * d.nb * 64 * 32 * 9, wp3 = (size_t)sp.n[2] * d.nb * 128 * 64 * 9;
   if (wp2 > wp) wp = wp2;
   if (wp3 > wp) wp = wp3;
-  const TcGeom tg = tc_geom(s.batch, s.bands, kTcSmCount);
-  const size_t wp_tc = (size_t)(tg.nsplit + 1) * 64 * s.bands * 9;
-  if (wp_tc > wp) wp = wp_tc;
+  const TcGeom tg = tc_geom(s.batch, s.bands, d.nb);
+  const size_t wp_tc[3] = {(size_t)tg.w1.nsplit * 64 * s.bands * 9, (size_t)tg.w2.nsplit * d.nb * 64 * 32 * 9,
+                           (size_t)tg.w3.nsplit * d.nb * 128 * 64 * 9};
+  for (int k = 0; k < 3; ++k)
+    if (wp_tc[k] > wp) wp = wp_tc[k];
   W.wpart = c.take(wp);
-  W.dzp = reinterpret_cast<__nv_bfloat16*>(c.take((size_t)2 * 8 * tg.rows * 4));
+  size_t dz16 = (size_t)2 * 8 * tg.rows11;                                     // conv1: 64 merged channels
+  if ((size_t)2 * d.nb * 8 * tg.rows11 > dz16) dz16 = (size_t)2 * d.nb * 8 * tg.rows11;   // conv2: 64 per branch
+  if ((size_t)2 * d.nb * 16 * tg.rows5 > dz16) dz16 = (size_t)2 * d.nb * 16 * tg.rows5;   // conv3: 128 per branch
+  W.dzp = take_bf16(c, dz16);
+  W.wdp[0] = take_bf16(c, (size_t)d.nb * 4 * (TcFprop<11, 32>::W_BYTES / 16));
+  W.wdp[1] = take_bf16(c, (size_t)d.nb * 8 * (TcFprop<5, 64>::W_BYTES / 16));
   W.wd[0] = c.take((size_t)d.nb * 32 * 9 * s.bands);
   W.wd[1] = c.take((size_t)d.nb * 64 * 9 * 32);
   W.wd[2] = c.take((size_t)d.nb * 128 * 9 * 64);
@@ -310,6 +334,44 @@ cudaError_t launch_wgrad(const ConvSrc& in, const ConvSrc& dz, float* part, int 
   dim3 grid((in.cin + CIK - 1) / CIK, nsplit, G);
   kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>(in, dz, part, B, per);
   return cudaGetLastError();
+}
+
+// ---- convolution launchers (conv_impl 1, tcgen05) ---------------------------------------
+template <int S, int NCO>
+cudaError_t run_tc_fprop(dta_ctx* ctx, cudaStream_t st, const __nv_bfloat16* xp, size_t rows, int nchunk, int chunks_per_group,
+                         const __nv_bfloat16* wp, int nstage, Ptr2 bias, int bias_split, float* out, int out_ctot, int cout_g, int B,
+                         int G) {
+  using Cfg = TcFprop<S, NCO>;
+  auto kern = tc_conv_fprop_kernel<S, NCO>;
+  cudaError_t e = allow_smem(kern, Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  const int ntiles = (int)((rows - 2 * kTcGuard) / Cfg::TILE);
+  const int nwork = ntiles * G;
+  const int grid = nwork < ctx->sm_count ? nwork : ctx->sm_count;
+  kern<<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(xp, rows, nchunk, chunks_per_group, wp, nstage, bias, bias_split, out, out_ctot, cout_g,
+                                                  B, ntiles, G);
+  return cudaGetLastError();
+}
+template <int S, class Cfg>
+cudaError_t run_tc_wgrad(cudaStream_t st, const __nv_bfloat16* dzp, int dz_chunks, const __nv_bfloat16* xp, int x_chunks, size_t rows,
+                         int cin_g, int cout_g, int G, const TcSplit& sp, float* part) {
+  auto kern = tc_conv_wgrad_kernel<S, Cfg>;
+  cudaError_t e = allow_smem(kern, Cfg::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  kern<<<dim3(sp.nslices, sp.nsplit, G), kTcThreads, Cfg::SMEM_BYTES, st>>>(dzp, dz_chunks, xp, x_chunks, rows, cin_g, cout_g, sp.nkstage,
+                                                                          sp.per, part);
+  return cudaGetLastError();
+}
+template <int S>
+cudaError_t run_tc_pack(dta_ctx* ctx, cudaStream_t st, const ConvSrc& src, int G, int B, int nchunk, size_t rows, __nv_bfloat16* dst) {
+  tc_pack_stream_kernel<S><<<ctx->sm_count * 8, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
+  return cudaGetLastError();
+}
+int run_bn_stats(dta_ctx* ctx, cudaStream_t st, const float* z, int B, int ctot, int hw, float* stats) {
+  const int per = hw > 100 ? 8 : 16;
+  const int nblk = (B + per - 1) / per;
+  bn_partial_stats_kernel<<<dim3(nblk, (ctot + 7) / 8), 256, 0, st>>>(z, B, ctot, hw, per, stats);
+  return nblk;
 }
 
 ConvSrc src_raw(const float* x, int cin, int hw) {
@@ -497,7 +559,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   // 1. pack parameters into kernel-friendly tables (a few MB, once per step)
   StageScope* pack_scope = new StageScope(ctx, "fwd.pack_params", st);
   struct ScopeDrop { StageScope*& p; ~ScopeDrop() { delete p; p = nullptr; } } pack_drop{pack_scope};
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 3 && ctx->conv_impl == 0; ++k) {
     Ptr2 w{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}};
     const int cin = k == 0 ? bands : kC[k - 1];
     pack_conv_w_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, kC[k], cin, k == 0 ? 1 : 0, L.wp[k]);
@@ -518,32 +580,32 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   cudaError_t e;
   int nblk = 0;
   // 2. block 1: conv1 over the crops (both branches share the read of x)
-  if (ctx->conv_impl == 1) {
+  const bool tcp = ctx->conv_impl == 1;
+  const TcGeom tg = tc_geom(B, bands, nb);
+#define DTA_TC_CHECK(expr, what)                                                                          \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e__)); \
+    ctx->launches++;                                                                                      \
+  } while (0)
+  auto conv_w = [&](int k) { return Ptr2{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}}; };
+  auto conv_b = [&](int k) { return Ptr2{{params->branch[0].conv[k].conv_b, nb > 1 ? params->branch[1].conv[k].conv_b : nullptr}}; };
+  if (tcp) {
     // tensor-core path: pack crops + weights, implicit GEMM, batch statistics of z
-    const TcGeom g = tc_geom(B, bands, kTcSmCount);
-    Ptr2 bias{{params->branch[0].conv[0].conv_b, nb > 1 ? params->branch[1].conv[0].conv_b : nullptr}};
-    Ptr2 w{{params->branch[0].conv[0].conv_w, nb > 1 ? params->branch[1].conv[0].conv_w : nullptr}};
     {
       StageScope sc(ctx, "fwd.conv1_pack", st);
-      tc_pack_stream_kernel<11><<<ctx->sm_count * 8, 256, 0, st>>>(src_raw(x, bands, kHW), 1, B, g.nchunk, g.rows, L.xp);
-      DTA_CHECK_LAUNCH(ctx, "tc_pack_stream(x)");
-      tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, st>>>(w, nb, 32, bands, g.nstage, W.wpf);
+      DTA_TC_CHECK(run_tc_pack<11>(ctx, st, src_raw(x, bands, kHW), 1, B, tg.nchunk1, tg.rows11, L.xp), "tc_pack_stream(x)");
+      tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, st>>>(conv_w(0), nb, 32, bands, tg.nstage1, 0, W.wpf[0]);
       DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
     }
     {
       StageScope sc(ctx, "fwd.conv1", st);
-      using Cfg = TcFprop<11, 64>;
-      auto kern = tc_conv_fprop_kernel<11, 64>;
-      if ((e = allow_smem(kern, Cfg::SMEM_BYTES)) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv1 fprop attr: ") + cudaGetErrorString(e));
-      const int grid = g.ntiles < ctx->sm_count ? g.ntiles : ctx->sm_count;
-      kern<<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(L.xp, g.rows, g.nchunk, W.wpf, g.nstage, bias, 32, L.z[0], nb * 32, B, g.ntiles);
-      DTA_CHECK_LAUNCH(ctx, "tc_conv_fprop");
+      DTA_TC_CHECK((run_tc_fprop<11, 64>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32, nb * 32, B, 1)),
+                   "tc_conv_fprop(conv1)");
     }
     if (shape->training) {
-      StageScope sc(ctx, "fwd.conv1_stats", st);
-      const int per = 8;
-      nblk = (B + per - 1) / per;
-      bn_partial_stats_kernel<<<dim3(nblk, (nb * 32 + 7) / 8), 256, 0, st>>>(L.z[0], B, nb * 32, kHW, per, W.stats);
+      StageScope sc(ctx, "fwd.bn_stats", st);
+      nblk = run_bn_stats(ctx, st, L.z[0], B, nb * 32, kHW, W.stats);
       DTA_CHECK_LAUNCH(ctx, "bn_partial_stats");
     }
   } else {
@@ -580,7 +642,24 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<1>");
   }
   // 3. block 2
-  {
+  if (tcp) {
+    ConvSrc src = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
+    {
+      StageScope sc(ctx, "fwd.conv2_pack", st);
+      DTA_TC_CHECK(run_tc_pack<11>(ctx, st, src, nb, B, nb * 4, tg.rows11, L.a1p), "tc_pack_stream(act1)");
+      tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, st>>>(conv_w(1), nb, 64, 32, 2, 1, W.wpf[1]);
+      DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
+    }
+    {
+      StageScope sc(ctx, "fwd.conv2", st);
+      DTA_TC_CHECK((run_tc_fprop<11, 64>(ctx, st, L.a1p, tg.rows11, nb * 4, 4, W.wpf[1], 2, conv_b(1), 64, L.z[1], nb * 64, 64, B, nb)), "tc_conv_fprop(conv2)");
+    }
+    if (shape->training) {
+      StageScope sc(ctx, "fwd.bn_stats", st);
+      nblk = run_bn_stats(ctx, st, L.z[1], B, nb * 64, kHW, W.stats);
+      DTA_CHECK_LAUNCH(ctx, "bn_partial_stats");
+    }
+  } else {
     StageScope sc(ctx, "fwd.conv2", st);
     ConvSrc src = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
     Ptr2 bias{{params->branch[0].conv[1].conv_b, nb > 1 ? params->branch[1].conv[1].conv_b : nullptr}};
@@ -598,7 +677,24 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<2>");
   }
   // 4. block 3
-  {
+  if (tcp) {
+    ConvSrc src = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
+    {
+      StageScope sc(ctx, "fwd.conv3_pack", st);
+      DTA_TC_CHECK(run_tc_pack<5>(ctx, st, src, nb, B, nb * 8, tg.rows5, L.a2p), "tc_pack_stream(act2)");
+      tc_pack_w_fprop_kernel<128><<<ctx->sm_count, 256, 0, st>>>(conv_w(2), nb, 128, 64, 4, 1, W.wpf[2]);
+      DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
+    }
+    {
+      StageScope sc(ctx, "fwd.conv3", st);
+      DTA_TC_CHECK((run_tc_fprop<5, 128>(ctx, st, L.a2p, tg.rows5, nb * 8, 8, W.wpf[2], 4, conv_b(2), 128, L.z[2], nb * 128, 128, B, nb)), "tc_conv_fprop(conv3)");
+    }
+    if (shape->training) {
+      StageScope sc(ctx, "fwd.bn_stats", st);
+      nblk = run_bn_stats(ctx, st, L.z[2], B, nb * 128, 25, W.stats);
+      DTA_CHECK_LAUNCH(ctx, "bn_partial_stats");
+    }
+  } else {
     StageScope sc(ctx, "fwd.conv3", st);
     ConvSrc src = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
     Ptr2 bias{{params->branch[0].conv[2].conv_b, nb > 1 ? params->branch[1].conv[2].conv_b : nullptr}};
@@ -674,11 +770,24 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   };
 
   // dgrad weight tables
+  const bool tcp = ctx->conv_impl == 1;
+  const TcGeom tg = tc_geom(B, bands, nb);
   for (int k = 1; k < 3; ++k) {
     Ptr2 w{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}};
-    pack_conv_wd_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, kC[k], kC[k - 1], 0, W.wd[k]);
+    if (tcp) {
+      if (k == 1) tc_pack_w_fprop_kernel<32><<<ctx->sm_count, 256, 0, st>>>(w, nb, 64, 32, 4, 2, W.wdp[0]);
+      else tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, st>>>(w, nb, 128, 64, 8, 2, W.wdp[1]);
+    } else {
+      pack_conv_wd_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, kC[k], kC[k - 1], 0, W.wd[k]);
+    }
     DTA_CHECK_LAUNCH(ctx, "pack_conv_wd");
   }
+#define DTA_TC_CHECK(expr, what)                                                                          \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e__)); \
+    ctx->launches++;                                                                                      \
+  } while (0)
   if (dx) {
     Ptr2 w{{params->branch[0].conv[0].conv_w, nb > 1 ? params->branch[1].conv[0].conv_w : nullptr}};
     pack_conv_wd_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, 32, bands, 1, W.wd[0]);
@@ -719,51 +828,54 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     DTA_CHECK_LAUNCH(ctx, "bn_bwd_finalize");
     return DTA_OK;
   };
-  // small parameter gradients of one attention block + head, reduced over the batch
+  // small parameter gradients (attention blocks + heads): batch reductions queued here and
+  // run by ONE batched_reduce_kernel launch at the end of the backward pass
+  ReduceTaskTable rtab{};
+  int rtiles = 0;
+  auto add_task = [&](const float* U, size_t ldu, const float* V, size_t ldv, int ni, int nj, float* out, size_t si, size_t sj) -> int {
+    if (out == nullptr) return DTA_OK;
+    if (rtab.n >= kMaxReduceTasks) return fail(ctx, DTA_ERR_UNSUPPORTED, "too many reduction tasks");
+    ReduceTask& t = rtab.t[rtab.n++];
+    t.U = U; t.V = V; t.out = out; t.ldu = (long long)ldu; t.ldv = (long long)ldv; t.si = (long long)si; t.sj = (long long)sj;
+    t.ni = ni; t.nj = nj; t.tile_begin = rtiles;
+    t.tiles_j = V ? (nj + 31) / 32 : 1;
+    rtiles += V ? ((ni + 31) / 32) * t.tiles_j : (ni + 31) / 32;
+    return DTA_OK;
+  };
   auto attn_param_grads = [&](int k) -> int {
-    StageScope sc(ctx, "bwd.small_param_grads", st);
     const int C = kC[k], ld = kProwLd[k];
-    for (int g = 0; g < nb; ++g) {
+    int r = DTA_OK;
+    for (int g = 0; g < nb && r == DTA_OK; ++g) {
       const dta_branch& gb = grads->branch[g];
-      const float* prow = W.prow + (size_t)g * ld;
+      const float* prow = W.prow[k] + (size_t)g * ld;
       const size_t prow_ld = (size_t)nb * ld;
       const float* att = L.att[k] + (size_t)g * 3 * kAttRow[k];
       const size_t att_ld = (size_t)nb * 3 * kAttRow[k];
       if (d.btype[g] == BR_SPECTRAL) {
         const int ks = k == 0 ? 3 : (k == 1 ? 5 : 7);
-        dim3 grid((C + 15) / 16, (C + 15) / 16), blk(16, 16);
         // dW2[i][j][mid] = sum_b du2[b][i] * h[b][j];  dW1[i][j][mid] = sum_b du1[b][i] * g[b][j]
-        if (gb.attn[k].w1) { outer_sum_kernel<<<grid, blk, 0, st>>>(prow, prow_ld, att + kAttRow[k], att_ld, B, C, C, gb.attn[k].w1 + ks / 2, (size_t)C * ks, ks); DTA_CHECK_LAUNCH(ctx, "outer_sum"); }
-        if (gb.attn[k].w0) { outer_sum_kernel<<<grid, blk, 0, st>>>(prow + C, prow_ld, att, att_ld, B, C, C, gb.attn[k].w0 + ks / 2, (size_t)C * ks, ks); DTA_CHECK_LAUNCH(ctx, "outer_sum"); }
-        if (gb.attn[k].b1) { colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(prow, prow_ld, B, C, gb.attn[k].b1, 1); DTA_CHECK_LAUNCH(ctx, "colsum"); }
-        if (gb.attn[k].b0) { colsum_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(prow + C, prow_ld, B, C, gb.attn[k].b0, 1); DTA_CHECK_LAUNCH(ctx, "colsum"); }
+        if (!r) r = add_task(prow, prow_ld, att + kAttRow[k], att_ld, C, C, gb.attn[k].w1 ? gb.attn[k].w1 + ks / 2 : nullptr, (size_t)C * ks, ks);
+        if (!r) r = add_task(prow + C, prow_ld, att, att_ld, C, C, gb.attn[k].w0 ? gb.attn[k].w0 + ks / 2 : nullptr, (size_t)C * ks, ks);
+        if (!r) r = add_task(prow, prow_ld, nullptr, 0, C, 1, gb.attn[k].b1, 1, 0);
+        if (!r) r = add_task(prow + C, prow_ld, nullptr, 0, C, 1, gb.attn[k].b0, 1, 0);
       } else if (d.btype[g] == BR_SPATIAL) {
         const int ks = k == 0 ? 7 : (k == 1 ? 5 : 3), kk = ks * ks;
-        auto cs = [&](const float* src, int n, float* dst) -> int {
-          if (!dst) return DTA_OK;
-          colsum_kernel<<<(n + 31) / 32, dim3(32, 8), 0, st>>>(src, prow_ld, B, n, dst, 1);
-          DTA_CHECK_LAUNCH(ctx, "colsum");
-          return DTA_OK;
-        };
-        int r;
-        if ((r = cs(prow, kk, gb.attn[k].w0)) || (r = cs(prow + kk, 1, gb.attn[k].b0)) || (r = cs(prow + kk + 1, kk, gb.attn[k].w1)) ||
-            (r = cs(prow + 2 * kk + 1, 1, gb.attn[k].b1)) || (r = cs(prow + 2 * kk + 2, C, gb.attn[k].pool_w)) ||
-            (r = cs(prow + 2 * kk + 2 + C, 1, gb.attn[k].pool_b)))
-          return r;
+        if (!r) r = add_task(prow, prow_ld, nullptr, 0, kk, 1, gb.attn[k].w0, 1, 0);
+        if (!r) r = add_task(prow + kk, prow_ld, nullptr, 0, 1, 1, gb.attn[k].b0, 1, 0);
+        if (!r) r = add_task(prow + kk + 1, prow_ld, nullptr, 0, kk, 1, gb.attn[k].w1, 1, 0);
+        if (!r) r = add_task(prow + 2 * kk + 1, prow_ld, nullptr, 0, 1, 1, gb.attn[k].b1, 1, 0);
+        if (!r) r = add_task(prow + 2 * kk + 2, prow_ld, nullptr, 0, C, 1, gb.attn[k].pool_w, 1, 0);
+        if (!r) r = add_task(prow + 2 * kk + 2 + C, prow_ld, nullptr, 0, 1, 1, gb.attn[k].pool_b, 1, 0);
       }
       const float* ds = head_ds(g, k);
       if (ds != nullptr && (d.btype[g] != BR_NONE || k == 2)) {
         const int F = d.btype[g] == BR_SPECTRAL ? C : (d.btype[g] == BR_SPATIAL ? 4 * C : 512);
         const float* feat = L.feat[k] + (size_t)g * kFeatLd[k];
-        if (gb.fc_w[k]) {
-          dim3 grid((F + 15) / 16, (classes + 15) / 16), blk(16, 16);
-          outer_sum_kernel<<<grid, blk, 0, st>>>(ds, classes, feat, (size_t)nb * kFeatLd[k], B, classes, F, gb.fc_w[k], F, 1);
-          DTA_CHECK_LAUNCH(ctx, "outer_sum");
-        }
-        if (gb.fc_b[k]) { colsum_kernel<<<(classes + 31) / 32, dim3(32, 8), 0, st>>>(ds, classes, B, classes, gb.fc_b[k], 1); DTA_CHECK_LAUNCH(ctx, "colsum"); }
+        if (!r) r = add_task(ds, classes, feat, (size_t)nb * kFeatLd[k], classes, F, gb.fc_w[k], F, 1);
+        if (!r) r = add_task(ds, classes, nullptr, 0, classes, 1, gb.fc_b[k], 1, 0);
       }
     }
-    return DTA_OK;
+    return r;
   };
   auto attn_prm = [&](int k) {
     AttnParams a = attn_params(params, L, d, k, vanilla && k == 2);
@@ -790,20 +902,32 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope* asc = new StageScope(ctx, "bwd.attn3", st);
     kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], L.bn_mean[2], L.bn_istd[2], attn_prm(2), classes, L.att[2], L.feat[2],
-                                              ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow);
+                                              ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow[2]);
     delete asc;
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<3>");
     if ((rc = attn_param_grads(2)) != DTA_OK) return rc;
     if ((rc = bn_bwd(2)) != DTA_OK) return rc;
     ConvSrc dz = src_dz(W.da[2], L.z[2], 128, nb * 128, 25, W.k0[2], W.k1[2], W.k2[2]);
     ConvSrc in = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
-    { StageScope sc(ctx, "bwd.conv3_wgrad", st); e = launch_wgrad<5, 32, 128, 8>(in, dz, W.wpart, B, sp.n[2], sp.per[2], nb, st); }
-    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 wgrad: ") + cudaGetErrorString(e));
-    ctx->launches++;
-    if ((rc = reduce_w(2, 64, sp.n[2])) != DTA_OK) return rc;
-    { StageScope sc(ctx, "bwd.conv3_dgrad", st); e = launch_fprop<5, 4, 4, 8, 64, 8>(dz, W.wd[2], Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, nullptr, B, nb, st, nullptr); }
-    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 dgrad: ") + cudaGetErrorString(e));
-    ctx->launches++;
+    if (tcp) {
+      { StageScope sc(ctx, "bwd.conv3_pack", st); DTA_TC_CHECK(run_tc_pack<5>(ctx, st, dz, nb, B, nb * 16, tg.rows5, W.dzp), "tc_pack_stream(dz3)"); }
+      {
+        StageScope sc(ctx, "bwd.conv3_wgrad", st);
+        DTA_TC_CHECK((run_tc_wgrad<5, WgradCfg3>(st, W.dzp, nb * 16, L.a2p, nb * 8, tg.rows5, 64, 128, nb, tg.w3, W.wpart)), "tc_conv_wgrad(conv3)");
+      }
+      if ((rc = reduce_w(2, 64, tg.w3.nsplit)) != DTA_OK) return rc;
+      StageScope sc(ctx, "bwd.conv3_dgrad", st);
+      DTA_TC_CHECK((run_tc_fprop<5, 64>(ctx, st, W.dzp, tg.rows5, nb * 16, 16, W.wdp[1], 8, Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, 64, B, nb)),
+                   "tc_conv_fprop(conv3 dgrad)");
+    } else {
+      { StageScope sc(ctx, "bwd.conv3_wgrad", st); e = launch_wgrad<5, 32, 128, 8>(in, dz, W.wpart, B, sp.n[2], sp.per[2], nb, st); }
+      if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 wgrad: ") + cudaGetErrorString(e));
+      ctx->launches++;
+      if ((rc = reduce_w(2, 64, sp.n[2])) != DTA_OK) return rc;
+      { StageScope sc(ctx, "bwd.conv3_dgrad", st); e = launch_fprop<5, 4, 4, 8, 64, 8>(dz, W.wd[2], Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, nullptr, B, nb, st, nullptr); }
+      if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 dgrad: ") + cudaGetErrorString(e));
+      ctx->launches++;
+    }
   }
   // ---- block 2 ----
   {
@@ -812,20 +936,32 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope* asc = new StageScope(ctx, "bwd.attn2", st);
     kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], L.bn_mean[1], L.bn_istd[1], attn_prm(1), classes, L.att[1], L.feat[1],
-                                              ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow);
+                                              ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow[1]);
     delete asc;
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<2>");
     if ((rc = attn_param_grads(1)) != DTA_OK) return rc;
     if ((rc = bn_bwd(1)) != DTA_OK) return rc;
     ConvSrc dz = src_dz(W.da[1], L.z[1], 64, nb * 64, 121, W.k0[1], W.k1[1], W.k2[1]);
     ConvSrc in = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
-    { StageScope sc(ctx, "bwd.conv2_wgrad", st); e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[1], sp.per[1], nb, st); }
-    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 wgrad: ") + cudaGetErrorString(e));
-    ctx->launches++;
-    if ((rc = reduce_w(1, 32, sp.n[1])) != DTA_OK) return rc;
-    { StageScope sc(ctx, "bwd.conv2_dgrad", st); e = launch_fprop<11, 1, 8, 4, 32, 16>(dz, W.wd[1], Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, nullptr, B, nb, st, nullptr); }
-    if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 dgrad: ") + cudaGetErrorString(e));
-    ctx->launches++;
+    if (tcp) {
+      { StageScope sc(ctx, "bwd.conv2_pack", st); DTA_TC_CHECK(run_tc_pack<11>(ctx, st, dz, nb, B, nb * 8, tg.rows11, W.dzp), "tc_pack_stream(dz2)"); }
+      {
+        StageScope sc(ctx, "bwd.conv2_wgrad", st);
+        DTA_TC_CHECK((run_tc_wgrad<11, WgradCfg2>(st, W.dzp, nb * 8, L.a1p, nb * 4, tg.rows11, 32, 64, nb, tg.w2, W.wpart)), "tc_conv_wgrad(conv2)");
+      }
+      if ((rc = reduce_w(1, 32, tg.w2.nsplit)) != DTA_OK) return rc;
+      StageScope sc(ctx, "bwd.conv2_dgrad", st);
+      DTA_TC_CHECK((run_tc_fprop<11, 32>(ctx, st, W.dzp, tg.rows11, nb * 8, 8, W.wdp[0], 4, Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, 32, B, nb)),
+                   "tc_conv_fprop(conv2 dgrad)");
+    } else {
+      { StageScope sc(ctx, "bwd.conv2_wgrad", st); e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[1], sp.per[1], nb, st); }
+      if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 wgrad: ") + cudaGetErrorString(e));
+      ctx->launches++;
+      if ((rc = reduce_w(1, 32, sp.n[1])) != DTA_OK) return rc;
+      { StageScope sc(ctx, "bwd.conv2_dgrad", st); e = launch_fprop<11, 1, 8, 4, 32, 16>(dz, W.wd[1], Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, nullptr, B, nb, st, nullptr); }
+      if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 dgrad: ") + cudaGetErrorString(e));
+      ctx->launches++;
+    }
   }
   // ---- block 1 ----
   {
@@ -834,7 +970,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope* asc = new StageScope(ctx, "bwd.attn1", st);
     kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], L.bn_mean[0], L.bn_istd[0], attn_prm(0), classes, L.att[0], L.feat[0],
-                                              ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow);
+                                              ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow[0]);
     delete asc;
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<1>");
     if ((rc = attn_param_grads(0)) != DTA_OK) return rc;
@@ -842,20 +978,11 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     ConvSrc dz = src_dz(W.da[0], L.z[0], nb * 32, nb * 32, 121, W.k0[0], W.k1[0], W.k2[0]);
     ConvSrc in = src_raw(x, bands, kHW);
     int conv1_nsplit = sp.n[0];
-    if (ctx->conv_impl == 1) {
-      const TcGeom g = tc_geom(B, bands, kTcSmCount);
-      {
-        StageScope sc(ctx, "bwd.conv1_pack", st);
-        tc_pack_stream_kernel<11><<<ctx->sm_count * 8, 256, 0, st>>>(dz, 1, B, 8, g.rows, W.dzp);
-        DTA_CHECK_LAUNCH(ctx, "tc_pack_stream(dz)");
-      }
+    if (tcp) {
+      { StageScope sc(ctx, "bwd.conv1_pack", st); DTA_TC_CHECK(run_tc_pack<11>(ctx, st, dz, 1, B, 8, tg.rows11, W.dzp), "tc_pack_stream(dz1)"); }
       StageScope sc(ctx, "bwd.conv1_wgrad", st);
-      auto kern = tc_conv_wgrad_kernel<11>;
-      if ((e = allow_smem(kern, TcWgrad::SMEM_BYTES)) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv1 wgrad attr: ") + cudaGetErrorString(e));
-      kern<<<dim3(g.nslices, g.nsplit), kTcThreads, TcWgrad::SMEM_BYTES, st>>>(W.dzp, L.xp, g.rows, g.nchunk, bands, nb * 32, g.nkstage,
-                                                                             g.stages_per_split, W.wpart);
-      e = cudaGetLastError();
-      conv1_nsplit = g.nsplit;
+      e = run_tc_wgrad<11, WgradCfg1>(st, W.dzp, 8, L.xp, tg.nchunk1, tg.rows11, bands, nb * 32, 1, tg.w1, W.wpart);
+      conv1_nsplit = tg.w1.nsplit;
     } else {
       StageScope sc(ctx, "bwd.conv1_wgrad", st);
       if (nb == 2) e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
@@ -865,6 +992,11 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     ctx->launches++;
     if ((rc = reduce_w(0, bands, conv1_nsplit)) != DTA_OK) return rc;
     if (dx) return fail(ctx, DTA_ERR_UNSUPPORTED, "gradient of the crops (dx) is not built yet; the reference feeds requires_grad=False inputs");
+  }
+  if (rtiles > 0) {
+    StageScope sc(ctx, "bwd.small_param_grads", st);
+    batched_reduce_kernel<<<rtiles, 256, 0, st>>>(rtab, B);
+    DTA_CHECK_LAUNCH(ctx, "batched_reduce");
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("backward: ") + cudaGetErrorString(e));

@@ -93,35 +93,49 @@ __global__ void tc_pack_stream_kernel(ConvSrc src, int G, int B, int nchunk, siz
   }
 }
 
-// Forward weights -> per 16-input-channel stage: [stage][tap 9][kchunk 2][row 2*NCO: hi co | lo co][8 ci].
-// w.p[br] = conv_layer.weight (cout_b, cin, 3, 3); merged output channel = br*cout_b + co (conv1 reads the
-// same crops for both branches); rows of absent channels are zero.
+// Forward-type weights -> per group, per 16-input-channel stage:
+//     dst[group][stage][tap 9][kchunk 2][row 2*NCO: hi rows | lo rows][8 k]
+// mode 0 (merged forward, conv1): one group, row = br*cout_b + co over both branches, k = ci
+// mode 1 (grouped forward)      : group = branch, row = co, k = ci
+// mode 2 (grouped input-gradient): group = branch, row = ci, k = co, tap flipped: the same GEMM
+//         kernel then computes dIn[ci][p] = sum_{co,tap} dz[co][p - s_tap] W[co][ci][tap]
+// w.p[br] = conv_layer.weight (cout_b, cin, 3, 3); rows / k beyond the tensor are zero.
 template <int NCO>
-__global__ void tc_pack_w_fprop_kernel(Ptr2 w, int nb, int cout_b, int cin, int nstage, __nv_bfloat16* __restrict__ dst) {
-  const size_t total = (size_t)nstage * 9 * 2 * (2 * NCO) * 8;
+__global__ void tc_pack_w_fprop_kernel(Ptr2 w, int nb, int cout_b, int cin, int nstage, int mode, __nv_bfloat16* __restrict__ dst) {
+  const int G = mode == 0 ? 1 : nb;
+  const size_t per_group = (size_t)nstage * 9 * 2 * (2 * NCO) * 8;
+  const size_t total = per_group * G;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i;
     const int j = (int)(r % 8); r /= 8;
     const int row = (int)(r % (2 * NCO)); r /= (2 * NCO);
     const int kc = (int)(r % 2); r /= 2;
     const int tap = (int)(r % 9); r /= 9;
-    const int stage = (int)r;
-    const int half = row / NCO, co = row - half * NCO;
-    const int ci = stage * 16 + kc * 8 + j;
+    const int stage = (int)(r % nstage); r /= nstage;
+    const int g = (int)r;
+    const int half = row / NCO, n = row - half * NCO;
+    const int k = stage * 16 + kc * 8 + j;
     float v = 0.f;
-    const int br = co / cout_b;
-    if (br < nb && ci < cin) v = __ldg(w.p[br] + ((size_t)(co - br * cout_b) * cin + ci) * 9 + tap);
+    if (mode == 0) {
+      const int br = n / cout_b;
+      if (br < nb && k < cin) v = __ldg(w.p[br] + ((size_t)(n - br * cout_b) * cin + k) * 9 + tap);
+    } else if (mode == 1) {
+      if (n < cout_b && k < cin) v = __ldg(w.p[g] + ((size_t)n * cin + k) * 9 + tap);
+    } else {
+      if (n < cin && k < cout_b) v = __ldg(w.p[g] + ((size_t)k * cin + n) * 9 + (8 - tap));
+    }
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     dst[i] = half == 0 ? h : __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
 
 // =======================================================================================
-// Forward: z[b][co][p] = bias[co] + sum_{ci,tap} x[b][ci][p + tap] * W[co][ci][tap]
-//   GEMM view: M = stream positions (tiles of 4 x 128), N = NCO output channels, K = ci (16 per stage) x 9 taps.
-//   Per (subtile, tap, 16 ci): MMA1  A_hi x [W_hi ; W_lo]  (N = 2*NCO)  -> cols [0,NCO) += hi*hi, [NCO,2NCO) += hi*lo
+// Forward-type convolution (also the input gradient, with mode-2 weights):
+//   out[b][g*cout_g + n][p] = bias + sum_{k,tap} in[b][g][k][p + tap] * Wp[g][n][k][tap]
+//   GEMM view: M = stream positions (tiles of SUB x 128), N = NCO, K = 16 input channels per stage x 9 taps.
+//   Per (subtile, tap, stage): MMA1  A_hi x [W_hi ; W_lo]  (N = 2*NCO)  -> cols [0,NCO) += hi*hi, [NCO,2NCO) += hi*lo
 //                              MMA2  A_lo x  W_hi          (N = NCO)    -> cols [0,NCO) += lo*hi
-//   Epilogue: z = cols[0,NCO) + cols[NCO,2NCO) + bias.
+//   Epilogue: out = cols[0,NCO) + cols[NCO,2NCO) + bias.  Work items = (group, tile), persistent CTAs.
 // =======================================================================================
 template <int S, int NCO>
 struct TcFprop {
@@ -140,9 +154,9 @@ struct TcFprop {
 
 template <int S, int NCO>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]*/, size_t rows, int nchunk,
-                     const __nv_bfloat16* __restrict__ wp /*[nstage][W_BYTES]*/, int nstage, Ptr2 bias, int bias_split,
-                     float* __restrict__ z /*[B][cout][S*S]*/, int cout, int B, int ntiles) {
+tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]*/, size_t rows, int nchunk, int chunks_per_group,
+                     const __nv_bfloat16* __restrict__ wp /*[G][nstage][W_BYTES]*/, int nstage, Ptr2 bias, int bias_split,
+                     float* __restrict__ out /*[B][out_ctot][S*S]*/, int out_ctot, int cout_g, int B, int ntiles, int G) {
   using Cfg = TcFprop<S, NCO>;
   using St = Stream<S>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -153,6 +167,7 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int lane = tid & 31;
+  const int nwork = ntiles * G;
 
   if (tid == 0) {
     for (int i = 0; i < Cfg::NSTAGE; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
@@ -171,7 +186,8 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
     // ---------------- producer: bulk copies global -> shared ----------------
     if (elect_one_sync()) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+        const int g = work / ntiles, tile = work - g * ntiles;
         const size_t row0 = (size_t)tile * Cfg::TILE;       // first staged row (= GUARD + q0 - GUARD)
         for (int ks = 0; ks < nstage; ++ks, ++it) {
           const int st = it % Cfg::NSTAGE;
@@ -184,8 +200,9 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
 #pragma unroll
             for (int kc = 0; kc < 2; ++kc)
               tc::bulk_g2s(sa + (size_t)(h * 2 + kc) * Cfg::AROWS * 16,
-                           xp + h * half_stride + ((size_t)(ks * 2 + kc) * rows + row0) * 8, Cfg::AROWS * 16, &full_bar[st]);
-          tc::bulk_g2s(sa + Cfg::A_BYTES, wp + (size_t)ks * (Cfg::W_BYTES / 2), Cfg::W_BYTES, &full_bar[st]);
+                           xp + h * half_stride + ((size_t)(g * chunks_per_group + ks * 2 + kc) * rows + row0) * 8, Cfg::AROWS * 16,
+                           &full_bar[st]);
+          tc::bulk_g2s(sa + Cfg::A_BYTES, wp + ((size_t)g * nstage + ks) * (Cfg::W_BYTES / 2), Cfg::W_BYTES, &full_bar[st]);
         }
       }
     }
@@ -195,7 +212,7 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
     constexpr uint32_t idesc1 = tc::make_idesc_bf16(128, 2 * NCO, 0, 0);
     constexpr uint32_t idesc2 = tc::make_idesc_bf16(128, NCO, 0, 0);
     uint32_t it = 0, tile_it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+    for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++tile_it) {
       tc::mbar_wait(&tmem_empty, (tile_it & 1) ^ 1);
       tc::fence_after_sync();
       for (int ks = 0; ks < nstage; ++ks, ++it) {
@@ -230,10 +247,11 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
       __syncwarp();
     }
   } else {
-    // ---------------- epilogue: TMEM -> registers -> z (NCHW fp32) ----------------
+    // ---------------- epilogue: TMEM -> registers -> out (NCHW fp32) ----------------
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     uint32_t tile_it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_it) {
+    for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++tile_it) {
+      const int g = work / ntiles, tile = work - g * ntiles;
       tc::mbar_wait(&tmem_full, tile_it & 1);
       tc::fence_after_sync();
 #pragma unroll 1
@@ -243,7 +261,7 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
         const int r = (int)(q - (long long)b * St::PC);
         const int yy = r / St::PT, xx = r - yy * St::PT;
         const bool valid = b < B && yy >= 1 && xx < S;
-        float* zrow = z + ((size_t)b * cout) * (S * S) + (yy - 1) * S + xx;
+        float* orow = out + ((size_t)b * out_ctot + (size_t)g * cout_g) * (S * S) + (yy - 1) * S + xx;
         const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + s * (2 * NCO);
 #pragma unroll 1
         for (int c0 = 0; c0 < NCO; c0 += 16) {
@@ -255,9 +273,10 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int ch = c0 + j;
-              if (ch < cout) {
-                const float bv = __ldg(bias.p[ch / bias_split] + (ch % bias_split));
-                zrow[(size_t)ch * (S * S)] = v0[j] + v1[j] + bv;
+              if (ch < cout_g) {
+                const int chg = g * cout_g + ch;
+                const float bv = bias.p[0] != nullptr ? __ldg(bias.p[chg / bias_split] + (chg % bias_split)) : 0.f;
+                orow[(size_t)ch * (S * S)] = v0[j] + v1[j] + bv;
               }
             }
           }
@@ -274,31 +293,39 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
 }
 
 // =======================================================================================
-// Weight gradient: dW[co][ci][tap] = sum_q dz[q][co] * x[q + s_tap][ci]   (q over the whole stream)
-//   GEMM view per tap: M = 2*64 rows [dz_hi co ; dz_lo co] (A, MN-major, shifted by -s_tap),
-//   N = 48 input channels of this CTA's slice (B, MN-major), K = stream positions (128 per stage).
-//   Two MMAs per (tap, 16 positions): B = x_hi and B = x_lo -> rows co hold dz_hi*x, rows 64+co dz_lo*x
-//   (all four partial products); 9 taps x 48 columns = 432 TMEM columns.  Split-K over the stream:
-//   part[split][co][ci][tap], summed in fixed order by wgrad_reduce_kernel.
+// Weight gradient: dW[g][co][ci][tap] = sum_q dz[q][g][co] * in[q + s_tap][g][ci]   (q over the whole stream)
+//   GEMM view per tap: M = 128 rows of dz (A, MN-major, start shifted by -s_tap), N = NCI input channels
+//   of this CTA's slice (B, MN-major), K = stream positions (KROWS per stage).
+//   STACK (64 output channels per group): A rows = [dz_hi co ; dz_lo co]; MMAs with B = in_hi and in_lo
+//       -> rows co hold dz_hi*in, rows 64+co hold dz_lo*in (all four partial products), summed in the epilogue.
+//   !STACK (128 output channels per group): MMAs (dz_hi,in_hi), (dz_hi,in_lo), (dz_lo,in_hi) into the same rows.
+//   9 taps x NCI columns of tensor memory.  Split-K over the stream: part[split][g][co][ci][tap], summed in
+//   fixed order by wgrad_reduce_kernel.
 // =======================================================================================
+template <int NCI_, int KROWS_, bool STACK_>
 struct TcWgrad {
-  static constexpr int NCI = 48;                          // input channels per CTA slice (6 chunks)
-  static constexpr int KROWS = 128;                       // stream positions per stage
-  static constexpr int AROWS = KROWS + 2 * kTcGuard;      // dz rows staged per chunk (taps reach +-13)
-  static constexpr int A_BYTES = 16 * AROWS * 16;         // [hi 8 | lo 8 chunks][AROWS][16 B]
-  static constexpr int B_BYTES = 2 * 6 * KROWS * 16;      // [half][6 chunks][KROWS][16 B]
+  static constexpr int NCI = NCI_;                         // input channels per CTA slice
+  static constexpr int KROWS = KROWS_;                     // stream positions per stage
+  static constexpr bool STACK = STACK_;
+  static constexpr int COUT = STACK ? 64 : 128;            // output channels per group
+  static constexpr int AROWS = KROWS + 2 * kTcGuard;       // dz rows staged per chunk
+  static constexpr int ACH = STACK ? 16 : 32;              // A chunks: [hi | lo]
+  static constexpr int A_BYTES = ACH * AROWS * 16;
+  static constexpr int BCH = NCI / 8;
+  static constexpr int B_BYTES = 2 * BCH * KROWS * 16;     // [half][BCH][KROWS][16 B]
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int NSTAGE = 3;
-  static constexpr int RED_BYTES = 64 * NCI * 4;          // lo-half partials for the epilogue
+  static constexpr int RED_BYTES = STACK ? 64 * NCI * 4 : 0;   // lo-half partials for the epilogue
   static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + RED_BYTES + 1024;
+  static_assert(9 * NCI <= 512 && NCI % 16 == 0, "9 taps x NCI fp32 columns must fit tensor memory");
+  static_assert(SMEM_BYTES <= 227 * 1024, "stage too large");
 };
 
-template <int S>
+template <int S, class Cfg>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][8][rows][8]*/, const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]*/,
-                     size_t rows, int nchunk, int cin, int cout, int nkstage_total, int stages_per_split,
-                     float* __restrict__ part /*[nsplit][cout][cin][9]*/) {
-  using Cfg = TcWgrad;
+tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows][8]*/, int dz_chunks,
+                     const __nv_bfloat16* __restrict__ xp /*[2][x_chunks][rows][8]*/, int x_chunks, size_t rows,
+                     int cin_g, int cout_g, int nkstage_total, int stages_per_split, float* __restrict__ part /*[nsplit][G][cout_g][cin_g][9]*/) {
   using St = Stream<S>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -309,10 +336,11 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][8][rows][8]*/, 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int lane = tid & 31;
-  const int slice = blockIdx.x, split = blockIdx.y;
+  const int slice = blockIdx.x, split = blockIdx.y, g = blockIdx.z, G = gridDim.z;
   const int ks_begin = split * stages_per_split;
   const int ks_end = min(nkstage_total, ks_begin + stages_per_split);
   const int nks = max(0, ks_end - ks_begin);
+  constexpr int DZ_CPG = Cfg::COUT / 8;            // dz chunks per group
 
   if (tid == 0) {
     for (int i = 0; i < Cfg::NSTAGE; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
@@ -327,7 +355,8 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][8][rows][8]*/, 
 
   if (warp == 0) {
     if (elect_one_sync()) {
-      const size_t dz_half = (size_t)8 * rows * 8, x_half = (size_t)nchunk * rows * 8;
+      const size_t dz_half = (size_t)dz_chunks * rows * 8, x_half = (size_t)x_chunks * rows * 8;
+      const int x_chunk0 = g * (cin_g / 8) + slice * Cfg::BCH;
       for (int i = 0; i < nks; ++i) {
         const int st = i % Cfg::NSTAGE;
         const uint32_t ph = (i / Cfg::NSTAGE) & 1;
@@ -336,15 +365,17 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][8][rows][8]*/, 
         unsigned char* sb = sa + Cfg::A_BYTES;
         const size_t k0 = (size_t)(ks_begin + i) * Cfg::KROWS;     // first stream position of the stage
         tc::mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
-        // dz rows [GUARD + k0 - GUARD, +AROWS)
-        for (int c = 0; c < 16; ++c)
-          tc::bulk_g2s(sa + (size_t)c * Cfg::AROWS * 16, dzp + (c / 8) * dz_half + ((size_t)(c % 8) * rows + k0) * 8, Cfg::AROWS * 16,
+        // dz rows [GUARD + k0 - GUARD, +AROWS): hi chunks then lo chunks
+        for (int c = 0; c < Cfg::ACH; ++c) {
+          const int h = c / DZ_CPG, cc = c - h * DZ_CPG;
+          tc::bulk_g2s(sa + (size_t)c * Cfg::AROWS * 16, dzp + h * dz_half + ((size_t)(g * DZ_CPG + cc) * rows + k0) * 8, Cfg::AROWS * 16,
                        &full_bar[st]);
-        // x rows [GUARD + k0, +KROWS) of this slice's 6 chunks
+        }
+        // input rows [GUARD + k0, +KROWS) of this slice's chunks
         for (int h = 0; h < 2; ++h)
-          for (int c = 0; c < 6; ++c)
-            tc::bulk_g2s(sb + (size_t)(h * 6 + c) * Cfg::KROWS * 16,
-                         xp + h * x_half + ((size_t)(slice * 6 + c) * rows + kTcGuard + k0) * 8, Cfg::KROWS * 16, &full_bar[st]);
+          for (int c = 0; c < Cfg::BCH; ++c)
+            tc::bulk_g2s(sb + (size_t)(h * Cfg::BCH + c) * Cfg::KROWS * 16,
+                         xp + h * x_half + ((size_t)(x_chunk0 + c) * rows + kTcGuard + k0) * 8, Cfg::KROWS * 16, &full_bar[st]);
       }
     }
   } else if (warp == 1) {
@@ -360,16 +391,19 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][8][rows][8]*/, 
       const uint64_t b_d = tc::sdesc_mnmajor(sa + Cfg::A_BYTES, Cfg::KROWS);
       const uint32_t a_lo32 = (uint32_t)a_d, a_hi32 = (uint32_t)(a_d >> 32);
       const uint32_t b_lo32 = (uint32_t)b_d, b_hi32 = (uint32_t)(b_d >> 32);
+      constexpr uint32_t A_LO_PLANE = 16 * Cfg::AROWS;          // !STACK: rows (16 B units) from dz_hi to dz_lo
+      constexpr uint32_t B_LO_PLANE = Cfg::BCH * Cfg::KROWS;    // in_hi -> in_lo
 #pragma unroll
       for (int kk = 0; kk < Cfg::KROWS / 16; ++kk) {
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const int arow = kTcGuard + kk * 16 - ((t / 3 - 1) * St::PT + (t % 3 - 1));   // dz row for x row kk*16
+          const int arow = kTcGuard + kk * 16 - ((t / 3 - 1) * St::PT + (t % 3 - 1));   // dz row for input row kk*16
           if (leader) {
-            tc::mma_bf16(tmem + t * Cfg::NCI, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + kk * 16, b_hi32), idesc,
-                         (i | kk) ? 1u : 0u);
-            tc::mma_bf16(tmem + t * Cfg::NCI, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + 6 * Cfg::KROWS + kk * 16, b_hi32),
-                         idesc, 1u);
+            const uint32_t dcol = tmem + t * Cfg::NCI;
+            tc::mma_bf16(dcol, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + kk * 16, b_hi32), idesc, (i | kk) ? 1u : 0u);
+            tc::mma_bf16(dcol, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + B_LO_PLANE + kk * 16, b_hi32), idesc, 1u);
+            if (!Cfg::STACK)
+              tc::mma_bf16(dcol, desc_from(a_lo32 + A_LO_PLANE + arow, a_hi32), desc_from(b_lo32 + kk * 16, b_hi32), idesc, 1u);
           }
         }
       }
@@ -379,7 +413,7 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][8][rows][8]*/, 
     if (leader) tc::mma_commit(&tmem_full);
     __syncwarp();
   } else {
-    // epilogue: rows co (< 64) + rows 64 + co -> part[split][co][ci][tap]
+    // epilogue -> part[split][g][co][ci][tap]
     const int quad = warp & 3;
     const int row = quad * 32 + lane;          // TMEM lane = A row
     if (nks > 0) {
@@ -396,18 +430,24 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][8][rows][8]*/, 
 #pragma unroll
         for (int j = 0; j < Cfg::NCI; ++j) v[j] = 0.f;
       }
-      if (row >= 64) {
+      if (Cfg::STACK) {
+        if (row >= 64) {
 #pragma unroll
-        for (int j = 0; j < Cfg::NCI; ++j) s_red[(row - 64) * Cfg::NCI + j] = v[j];
+          for (int j = 0; j < Cfg::NCI; ++j) s_red[(row - 64) * Cfg::NCI + j] = v[j];
+        }
+        epi_bar_sync();
+        if (row < 64) {
+#pragma unroll
+          for (int j = 0; j < Cfg::NCI; ++j) v[j] += s_red[row * Cfg::NCI + j];
+        }
       }
-      epi_bar_sync();
-      if (row < 64 && row < cout) {
-        float* dst = part + (((size_t)split * cout + row) * cin + (size_t)slice * Cfg::NCI) * 9 + t;
+      if (row < Cfg::COUT && row < cout_g) {
+        float* dst = part + ((((size_t)split * G + g) * cout_g + row) * cin_g + (size_t)slice * Cfg::NCI) * 9 + t;
 #pragma unroll
         for (int j = 0; j < Cfg::NCI; ++j)
-          if (slice * Cfg::NCI + j < cin) dst[(size_t)j * 9] = v[j] + s_red[row * Cfg::NCI + j];
+          if (slice * Cfg::NCI + j < cin_g) dst[(size_t)j * 9] = v[j];
       }
-      epi_bar_sync();
+      if (Cfg::STACK) epi_bar_sync();
     }
   }
   tc::fence_before_sync();

@@ -238,6 +238,82 @@ __global__ void alpha_grad_kernel(const float* __restrict__ djoint, const float*
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// All small parameter gradients of a backward pass in ONE launch.  Each task is a batch
+// reduction  out[i*si + j*sj] = sum_b U[b*ldu + i] * V[b*ldv + j]  (V == nullptr: column sums of
+// U, nj = 1): attention / classifier weight and bias gradients.  A CTA owns one 32x32 output
+// tile (outer products) or 32 columns (column sums) and walks the batch in fixed order, so
+// the result is deterministic.
+// ---------------------------------------------------------------------------------------
+struct ReduceTask {
+  const float* U;
+  const float* V;
+  float* out;
+  long long ldu, ldv, si, sj;
+  int ni, nj;
+  int tile_begin;   // first CTA of this task
+  int tiles_j;      // tiles along j
+};
+constexpr int kMaxReduceTasks = 96;
+struct ReduceTaskTable {
+  ReduceTask t[kMaxReduceTasks];
+  int n;
+};
+
+__global__ void __launch_bounds__(256) batched_reduce_kernel(const __grid_constant__ ReduceTaskTable tab, int B) {
+  __shared__ float su[32][33];
+  __shared__ float sv[32][33];
+  int ti = 0;
+  while (ti + 1 < tab.n && tab.t[ti + 1].tile_begin <= (int)blockIdx.x) ++ti;
+  const ReduceTask& T = tab.t[ti];
+  const int tile = blockIdx.x - T.tile_begin;
+  const int tid = threadIdx.x;
+  if (T.V == nullptr) {
+    // column sums: 32 columns x 8 batch slices
+    const int tx = tid & 31, ty = tid >> 5;
+    const int j = tile * 32 + tx;
+    float a = 0.f;
+    if (j < T.ni)
+      for (int b = ty; b < B; b += 8) a += __ldg(T.U + (size_t)b * T.ldu + j);
+    su[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && j < T.ni) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += su[k][tx];
+      T.out[(size_t)j * T.si] = t;
+    }
+    return;
+  }
+  const int i0 = (tile / T.tiles_j) * 32, j0 = (tile % T.tiles_j) * 32;
+  const int tx = tid & 15, ty = tid >> 4;   // each thread: outputs (2*ty + {0,1}, 2*tx + {0,1})
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    for (int e = tid; e < 32 * 32; e += 256) {
+      const int bb = e >> 5, k = e & 31;
+      const int b = b0 + bb;
+      su[bb][k] = (b < B && i0 + k < T.ni) ? __ldg(T.U + (size_t)b * T.ldu + i0 + k) : 0.f;
+      sv[bb][k] = (b < B && j0 + k < T.nj) ? __ldg(T.V + (size_t)b * T.ldv + j0 + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int bb = 0; bb < 32; ++bb) {
+      const float u0 = su[bb][2 * ty], u1 = su[bb][2 * ty + 1];
+      const float v0 = sv[bb][2 * tx], v1 = sv[bb][2 * tx + 1];
+      acc[0][0] = fmaf(u0, v0, acc[0][0]); acc[0][1] = fmaf(u0, v1, acc[0][1]);
+      acc[1][0] = fmaf(u1, v0, acc[1][0]); acc[1][1] = fmaf(u1, v1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + c;
+      if (i < T.ni && j < T.nj) T.out[(size_t)i * T.si + (size_t)j * T.sj] = acc[a][c];
+    }
+}
+
 __global__ void fill_zero_kernel(float* __restrict__ p, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }

@@ -110,6 +110,28 @@ def test_cuda_matches_oracle(kind, bands, classes, batch, regime, training):
         assert err <= 1e-5 + 1e-3 * scale + 8.0 * sens[k], f"{k}: err {err:.3e} scale {scale:.3e} sens {sens[k]:.3e}"
 
 
+@pytest.mark.parametrize("kind,bands,classes,batch,regime", [("hang2020", 369, 50, 16, "R2"), ("spatial", 40, 6, 9, "R2")])
+def test_fp32_simt_path_matches_oracle(kind, bands, classes, batch, regime):
+    """conv_impl 0 (exact-fp32 CUDA-core convolutions) stays a supported, tighter cross-check path."""
+    from deeptreeattention_b200 import _capi
+    table = orc.init_params(kind, bands, classes, 77, perturb_bn=True)
+    x, y = orc.make_inputs(batch, bands, classes, 77)
+    rloss, rres, rheads, rgrads, _ = orc.step(kind, table, x, y, regime=regime, training=True)
+    sens = gu.oracle_sensitivity(kind, table, x, y, regime, True, rgrads, draws=2)
+    _capi.set_option(0, "conv_impl", 0)
+    try:
+        loss, res, heads, grads, _ = run_cuda(kind, bands, classes, table, x, y, regime, True)
+    finally:
+        _capi.set_option(0, "conv_impl", 1)
+    for h, rh in zip(heads, rheads):
+        np.testing.assert_allclose(h, rh.detach().numpy(), rtol=0, atol=2e-5)
+    for k, rg in rgrads.items():
+        if rg is None:
+            continue
+        err = float((grads[k].double() - rg.double()).abs().max())
+        assert err <= 1e-5 + 1e-4 * float(rg.abs().max()) + 8.0 * sens[k], k
+
+
 def test_dead_conv1d_taps_get_exact_zero():
     table = orc.init_params("spectral", 16, 5, 3)
     x, y = orc.make_inputs(6, 16, 5, 3)
