@@ -163,9 +163,9 @@ FwdWork layout_fwd(const dta_shape& s, const NetDesc& d, void* base) {
   FwdWork W{};
   Carver c(base);
   W.stats = c.take((size_t)s.batch * d.nb * 128 * 2);
-  W.wpf[0] = take_bf16(c, (size_t)tc_geom(s.batch, s.bands, d.nb).nstage1 * (TcFprop<11, 64>::W_BYTES / 16));
-  W.wpf[1] = take_bf16(c, (size_t)d.nb * 2 * (TcFprop<11, 64>::W_BYTES / 16));
-  W.wpf[2] = take_bf16(c, (size_t)d.nb * 4 * (TcFprop<5, 128>::W_BYTES / 16));
+  W.wpf[0] = take_bf16(c, (size_t)tc_geom(s.batch, s.bands, d.nb).nstage1 * (TcFprop<11, 64, false>::W_BYTES / 16));
+  W.wpf[1] = take_bf16(c, (size_t)d.nb * 2 * (TcFprop<11, 64, false>::W_BYTES / 16));
+  W.wpf[2] = take_bf16(c, (size_t)d.nb * 4 * (TcFprop<5, 128, true>::W_BYTES / 16));
   W.bytes = c.off;
   return W;
 }
@@ -223,8 +223,8 @@ BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
   if ((size_t)2 * d.nb * 8 * tg.rows11 > dz16) dz16 = (size_t)2 * d.nb * 8 * tg.rows11;   // conv2: 64 per branch
   if ((size_t)2 * d.nb * 16 * tg.rows5 > dz16) dz16 = (size_t)2 * d.nb * 16 * tg.rows5;   // conv3: 128 per branch
   W.dzp = take_bf16(c, dz16);
-  W.wdp[0] = take_bf16(c, (size_t)d.nb * 4 * (TcFprop<11, 32>::W_BYTES / 16));
-  W.wdp[1] = take_bf16(c, (size_t)d.nb * 8 * (TcFprop<5, 64>::W_BYTES / 16));
+  W.wdp[0] = take_bf16(c, (size_t)d.nb * 4 * (TcFprop<11, 32, true>::W_BYTES / 16));
+  W.wdp[1] = take_bf16(c, (size_t)d.nb * 8 * (TcFprop<5, 64, true>::W_BYTES / 16));
   W.wd[0] = c.take((size_t)d.nb * 32 * 9 * s.bands);
   W.wd[1] = c.take((size_t)d.nb * 64 * 9 * 32);
   W.wd[2] = c.take((size_t)d.nb * 128 * 9 * 64);
@@ -337,18 +337,18 @@ cudaError_t launch_wgrad(const ConvSrc& in, const ConvSrc& dz, float* part, int 
 }
 
 // ---- convolution launchers (conv_impl 1, tcgen05) ---------------------------------------
-template <int S, int NCO>
+template <int S, int NCO, bool ACC2>
 cudaError_t run_tc_fprop(dta_ctx* ctx, cudaStream_t st, const __nv_bfloat16* xp, size_t rows, int nchunk, int chunks_per_group,
                          const __nv_bfloat16* wp, int nstage, Ptr2 bias, int bias_split, float* out, int out_ctot, int cout_g, int B,
                          int G) {
-  using Cfg = TcFprop<S, NCO>;
-  auto kern = tc_conv_fprop_kernel<S, NCO>;
+  using Cfg = TcFprop<S, NCO, ACC2>;
+  auto kern = tc_conv_fprop_kernel<S, NCO, ACC2>;
   cudaError_t e = allow_smem(kern, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   const int ntiles = (int)((rows - 2 * kTcGuard) / Cfg::TILE);
   const int nwork = ntiles * G;
   const int grid = nwork < ctx->sm_count ? nwork : ctx->sm_count;
-  kern<<<grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(xp, rows, nchunk, chunks_per_group, wp, nstage, bias, bias_split, out, out_ctot, cout_g,
+  kern<<<grid, kTcFpropThreads, Cfg::SMEM_BYTES, st>>>(xp, rows, nchunk, chunks_per_group, wp, nstage, bias, bias_split, out, out_ctot, cout_g,
                                                   B, ntiles, G);
   return cudaGetLastError();
 }
@@ -600,7 +600,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     }
     {
       StageScope sc(ctx, "fwd.conv1", st);
-      DTA_TC_CHECK((run_tc_fprop<11, 64>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32, nb * 32, B, 1)),
+      DTA_TC_CHECK((run_tc_fprop<11, 64, false>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32, nb * 32, B, 1)),
                    "tc_conv_fprop(conv1)");
     }
     if (shape->training) {
@@ -652,7 +652,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     }
     {
       StageScope sc(ctx, "fwd.conv2", st);
-      DTA_TC_CHECK((run_tc_fprop<11, 64>(ctx, st, L.a1p, tg.rows11, nb * 4, 4, W.wpf[1], 2, conv_b(1), 64, L.z[1], nb * 64, 64, B, nb)), "tc_conv_fprop(conv2)");
+      DTA_TC_CHECK((run_tc_fprop<11, 64, true>(ctx, st, L.a1p, tg.rows11, nb * 4, 4, W.wpf[1], 2, conv_b(1), 64, L.z[1], nb * 64, 64, B, nb)), "tc_conv_fprop(conv2)");
     }
     if (shape->training) {
       StageScope sc(ctx, "fwd.bn_stats", st);
@@ -687,7 +687,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     }
     {
       StageScope sc(ctx, "fwd.conv3", st);
-      DTA_TC_CHECK((run_tc_fprop<5, 128>(ctx, st, L.a2p, tg.rows5, nb * 8, 8, W.wpf[2], 4, conv_b(2), 128, L.z[2], nb * 128, 128, B, nb)), "tc_conv_fprop(conv3)");
+      DTA_TC_CHECK((run_tc_fprop<5, 128, true>(ctx, st, L.a2p, tg.rows5, nb * 8, 8, W.wpf[2], 4, conv_b(2), 128, L.z[2], nb * 128, 128, B, nb)), "tc_conv_fprop(conv3)");
     }
     if (shape->training) {
       StageScope sc(ctx, "fwd.bn_stats", st);
@@ -917,7 +917,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
       }
       if ((rc = reduce_w(2, 64, tg.w3.nsplit)) != DTA_OK) return rc;
       StageScope sc(ctx, "bwd.conv3_dgrad", st);
-      DTA_TC_CHECK((run_tc_fprop<5, 64>(ctx, st, W.dzp, tg.rows5, nb * 16, 16, W.wdp[1], 8, Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, 64, B, nb)),
+      DTA_TC_CHECK((run_tc_fprop<5, 64, true>(ctx, st, W.dzp, tg.rows5, nb * 16, 16, W.wdp[1], 8, Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, 64, B, nb)),
                    "tc_conv_fprop(conv3 dgrad)");
     } else {
       { StageScope sc(ctx, "bwd.conv3_wgrad", st); e = launch_wgrad<5, 32, 128, 8>(in, dz, W.wpart, B, sp.n[2], sp.per[2], nb, st); }
@@ -951,7 +951,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
       }
       if ((rc = reduce_w(1, 32, tg.w2.nsplit)) != DTA_OK) return rc;
       StageScope sc(ctx, "bwd.conv2_dgrad", st);
-      DTA_TC_CHECK((run_tc_fprop<11, 32>(ctx, st, W.dzp, tg.rows11, nb * 8, 8, W.wdp[0], 4, Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, 32, B, nb)),
+      DTA_TC_CHECK((run_tc_fprop<11, 32, true>(ctx, st, W.dzp, tg.rows11, nb * 8, 8, W.wdp[0], 4, Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, 32, B, nb)),
                    "tc_conv_fprop(conv2 dgrad)");
     } else {
       { StageScope sc(ctx, "bwd.conv2_wgrad", st); e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[1], sp.per[1], nb, st); }

@@ -137,10 +137,17 @@ __global__ void tc_pack_w_fprop_kernel(Ptr2 w, int nb, int cout_b, int cin, int 
 //                              MMA2  A_lo x  W_hi          (N = NCO)    -> cols [0,NCO) += lo*hi
 //   Epilogue: out = cols[0,NCO) + cols[NCO,2NCO) + bias.  Work items = (group, tile), persistent CTAs.
 // =======================================================================================
-template <int S, int NCO>
+constexpr int kTcFpropThreads = 320;   // warp 0 producer, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane quadrant)
+
+// ACC2: two accumulator stages of half a tile each, so the epilogue of one tile overlaps the MMAs of the
+// next (used where K is short: conv2, conv3 and the input gradients); conv1 (K = 24 stages) keeps one
+// full-size accumulator so the packed weights are re-streamed half as often.
+template <int S, int NCO, bool ACC2>
 struct TcFprop {
   using St = Stream<S>;
-  static constexpr int SUB = 512 / (2 * NCO);            // 128-position subtiles per tile (all 512 TMEM columns)
+  static constexpr int NACC = ACC2 ? 2 : 1;
+  static constexpr int ACC_COLS = 512 / NACC;
+  static constexpr int SUB = ACC_COLS / (2 * NCO);       // 128-position subtiles per tile
   static constexpr int TILE = SUB * 128;
   static constexpr int AROWS = TILE + 2 * kTcGuard;      // rows staged per chunk
   static constexpr int A_BYTES = 2 * 2 * AROWS * 16;     // [half][kchunk][AROWS][16 B]
@@ -148,21 +155,23 @@ struct TcFprop {
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int NSTAGE = (222 * 1024) / STAGE_BYTES >= 4 ? 4 : (222 * 1024) / STAGE_BYTES;
   static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 1024;
+  static_assert(SUB >= 1, "accumulator stage too small");
   static_assert(NSTAGE >= 2, "stage too large");
   static_assert(kTcGuard >= St::PT + 1, "guard must cover the largest tap shift");
 };
 
-template <int S, int NCO>
-__global__ void __launch_bounds__(kTcThreads, 1)
+template <int S, int NCO, bool ACC2>
+__global__ void __launch_bounds__(kTcFpropThreads, 1)
 tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]*/, size_t rows, int nchunk, int chunks_per_group,
                      const __nv_bfloat16* __restrict__ wp /*[G][nstage][W_BYTES]*/, int nstage, Ptr2 bias, int bias_split,
                      float* __restrict__ out /*[B][out_ctot][S*S]*/, int out_ctot, int cout_g, int B, int ntiles, int G) {
-  using Cfg = TcFprop<S, NCO>;
+  using Cfg = TcFprop<S, NCO, ACC2>;
   using St = Stream<S>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  __shared__ uint64_t full_bar[4], empty_bar[4], tmem_full, tmem_empty;
+  __shared__ uint64_t full_bar[4], empty_bar[4], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[2][NCO];
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -171,8 +180,7 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
 
   if (tid == 0) {
     for (int i = 0; i < Cfg::NSTAGE; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
-    tc::mbar_init(&tmem_full, 1);
-    tc::mbar_init(&tmem_empty, 4);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 8); }
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, 512);
@@ -213,8 +221,10 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
     constexpr uint32_t idesc2 = tc::make_idesc_bf16(128, NCO, 0, 0);
     uint32_t it = 0, tile_it = 0;
     for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++tile_it) {
-      tc::mbar_wait(&tmem_empty, (tile_it & 1) ^ 1);
+      const uint32_t acc = tile_it % Cfg::NACC, acc_use = tile_it / Cfg::NACC;
+      tc::mbar_wait(&tmem_empty[acc], (acc_use & 1) ^ 1);
       tc::fence_after_sync();
+      const uint32_t dbase = tmem + acc * Cfg::ACC_COLS;
       for (int ks = 0; ks < nstage; ++ks, ++it) {
         const int st = it % Cfg::NSTAGE;
         const uint32_t ph = (it / Cfg::NSTAGE) & 1;
@@ -234,25 +244,38 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
             const int shift = kTcGuard + s * 128 + (t / 3 - 1) * St::PT + (t % 3 - 1);   // rows == 16-byte units
             const uint32_t boff = t * (2 * (2 * NCO));                                    // 16-byte units per tap
             if (leader) {
-              tc::mma_bf16(tmem + s * (2 * NCO), desc_from(a_lo32 + shift, a_hi32), desc_from(b_lo32 + boff, b_hi32), idesc1,
+              tc::mma_bf16(dbase + s * (2 * NCO), desc_from(a_lo32 + shift, a_hi32), desc_from(b_lo32 + boff, b_hi32), idesc1,
                            (ks | t) ? 1u : 0u);
-              tc::mma_bf16(tmem + s * (2 * NCO), desc_from(al_lo32 + shift, a_hi32), desc_from(b_lo32 + boff, b_hi32), idesc2, 1u);
+              tc::mma_bf16(dbase + s * (2 * NCO), desc_from(al_lo32 + shift, a_hi32), desc_from(b_lo32 + boff, b_hi32), idesc2, 1u);
             }
           }
         }
         __syncwarp();
         if (leader) tc::mma_commit(&empty_bar[st]);
       }
-      if (leader) tc::mma_commit(&tmem_full);
+      if (leader) tc::mma_commit(&tmem_full[acc]);
       __syncwarp();
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> out (NCHW fp32) ----------------
+    const int ew = warp - 2;                   // 0..7
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int chalf = ew >> 2;                 // which half of the output channels
+    const int et = tid - 64;                   // 0..255
+    constexpr int CH_PER = NCO / 2;
     uint32_t tile_it = 0;
     for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++tile_it) {
       const int g = work / ntiles, tile = work - g * ntiles;
-      tc::mbar_wait(&tmem_full, tile_it & 1);
+      const uint32_t acc = tile_it % Cfg::NACC, acc_use = tile_it / Cfg::NACC;
+      float* sb = s_bias[tile_it & 1];
+      if (et < NCO) {
+        float bv = 0.f;
+        const int chg = g * cout_g + et;
+        if (et < cout_g && bias.p[0] != nullptr) bv = __ldg(bias.p[chg / bias_split] + (chg % bias_split));
+        sb[et] = bv;
+      }
+      asm volatile("bar.sync 1, 256;" : : : "memory");
+      tc::mbar_wait(&tmem_full[acc], acc_use & 1);
       tc::fence_after_sync();
 #pragma unroll 1
       for (int s = 0; s < Cfg::SUB; ++s) {
@@ -262,29 +285,25 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
         const int yy = r / St::PT, xx = r - yy * St::PT;
         const bool valid = b < B && yy >= 1 && xx < S;
         float* orow = out + ((size_t)b * out_ctot + (size_t)g * cout_g) * (S * S) + (yy - 1) * S + xx;
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + s * (2 * NCO);
-#pragma unroll 1
-        for (int c0 = 0; c0 < NCO; c0 += 16) {
-          float v0[16], v1[16];
-          tc::tmem_ld16(taddr + c0, v0);
-          tc::tmem_ld16(taddr + NCO + c0, v1);
-          tc::tmem_ld_wait();
-          if (valid) {
+        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * Cfg::ACC_COLS + s * (2 * NCO);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int ch = c0 + j;
-              if (ch < cout_g) {
-                const int chg = g * cout_g + ch;
-                const float bv = bias.p[0] != nullptr ? __ldg(bias.p[chg / bias_split] + (chg % bias_split)) : 0.f;
-                orow[(size_t)ch * (S * S)] = v0[j] + v1[j] + bv;
-              }
+        for (int cc = 0; cc < CH_PER; cc += 16) {
+          const int c0 = chalf * CH_PER + cc;
+          if (c0 < cout_g) {
+            float v0[16], v1[16];
+            tc::tmem_ld16(taddr + c0, v0);
+            tc::tmem_ld16(taddr + NCO + c0, v1);
+            tc::tmem_ld_wait();
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) orow[(size_t)(c0 + j) * (S * S)] = v0[j] + v1[j] + sb[c0 + j];
             }
           }
         }
       }
       tc::fence_before_sync();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tmem_empty);
+      if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
     }
   }
   tc::fence_before_sync();
