@@ -234,14 +234,27 @@ def run_b200(args):
     x_dev = x_host.to(dev)
     params = list(model.parameters())
 
+    from deeptreeattention_b200.loss import cross_entropy_heads
+
     def train_step(xd):
         for p in params:
             p.grad = None
         joint = model(xd)
-        loss = loss_of(args.regime, joint, model.head_scores, y_dev)
+        # the library's fused weighted cross-entropy (== sum of F.cross_entropy over the heads, tests/test_gpu_parity.py)
+        loss = cross_entropy_heads([joint] if args.regime == "R1" else model.head_scores, y_dev)
         loss.backward()
         sync.sync()
         return loss
+
+    step_fn = train_step
+    if args.graph:
+        from deeptreeattention_b200.graph import GraphedTrainStep
+        graphed = GraphedTrainStep(model, x_dev, y_dev,
+                                   lambda m, out, y: cross_entropy_heads([out] if args.regime == "R1" else m.head_scores, y),
+                                   after_backward=sync.sync)
+
+        def step_fn(xd):
+            return graphed(xd)
 
     def barrier():
         if world > 1:
@@ -256,32 +269,40 @@ def run_b200(args):
 
     # ---- device-resident timing -------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        train_step(x_dev)
+        step_fn(x_dev)
     torch.cuda.synchronize()
-    _capi.set_option(local, "profile", 1)
-    _capi.profile_read(local, reset=True)
+    # kernels launched per step by the library (host-side counters of the three C-ABI calls of an eager step)
+    model(x_dev)
+    fwd_launches = _capi.get_option(local, "launches")
+    train_step(x_dev)
+    bwd_launches = _capi.get_option(local, "launches")
+    torch.cuda.synchronize()
+    launches = (fwd_launches + 3 + bwd_launches) * args.steps
+    if not args.graph:
+        _capi.set_option(local, "profile", 1)
+        _capi.profile_read(local, reset=True)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    launches = 0
     barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        train_step(x_dev)
-        launches += _capi.get_option(local, "launches")      # backward's count (host counter)
+        step_fn(x_dev)
     e1.record()
     torch.cuda.synchronize(); barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clock_rec = clocks.stop() if rank == 0 else None
+    if args.graph:
+        # per-stage CUDA-event timing cannot run inside a replayed graph: same kernels, same buffers, one
+        # eager pass of `steps` steps right after the timed region, events on the launching stream
+        _capi.set_option(local, "profile", 1)
+        _capi.profile_read(local, reset=True)
+        for _ in range(args.steps):
+            train_step(x_dev)
+        torch.cuda.synchronize()
     stages = _capi.profile_read(local, reset=True)
     _capi.set_option(local, "profile", 0)
-    # forward's launch count: one extra forward outside the timed region
-    with torch.no_grad():
-        model(x_dev)
-    fwd_launches = _capi.get_option(local, "launches")
-    torch.cuda.synchronize()
-    launches += fwd_launches * args.steps
     ms_step = ms_total / args.steps
     value = world * B / (ms_step * 1e-3)
 
@@ -307,7 +328,7 @@ def run_b200(args):
             if i + 1 < n:
                 prefetch(i + 1)                      # next step's crops cross PCIe under this step's math
             torch.cuda.current_stream().wait_event(ready[i & 1])
-            loss = train_step(x_buf[i & 1])
+            loss = step_fn(x_buf[i & 1])
             consumed[i & 1].record(torch.cuda.current_stream())
             last = loss.item()                       # D2H read of the step's result
         return last
@@ -350,6 +371,8 @@ def run_b200(args):
     roof["step_tensor"] = {"achieved": (value / world) * step_flops_per_crop(bands) / 1e12, "peak": peaks["bf16_tflops_sustained"],
                            "unit": "TFLOP/s", "frac": (value / world) * step_flops_per_crop(bands) / 1e12 / peaks["bf16_tflops_sustained"],
                            "flops_per_crop": step_flops_per_crop(bands)}
+    roof["stage_timing"] = ("eager pass after the timed region (graph replay cannot carry events)" if args.graph
+                            else "inside the timed region")
     roof["stages_ms_per_step"] = {k: round(v, 4) for k, v in sorted(stage_ms.items(), key=lambda kv: -kv[1])}
     traffic_file = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(traffic_file):
@@ -376,7 +399,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": f"Hang2020(bands={bands}, classes={classes}) fwd+CE({args.regime})+bwd"
                                + ("+grad all-reduce" if world > 1 else "") + f", {B} crops per GPU per step",
-                   "regime": args.regime, "batch_per_gpu": B, "global_batch": B * world,
+                   "regime": args.regime, "launch": "cuda-graph replay" if args.graph else "eager", "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"dp{world}", "l2": f"crops per step = {B * bands * 484 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
                    if B * bands * 484 > 126e6 else "flush: none (inputs smaller than L2)"},
         "roofline": roof, "cpu_baseline": cpu, "clocks": clock_rec,
@@ -400,6 +423,7 @@ def main():
     ap.add_argument("--classes", type=int, default=50)
     ap.add_argument("--regime", default="R2", choices=["R1", "R2"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -54,7 +54,8 @@ class StageTime(C.Structure):
 
 
 EXPORTS = ["dta_abi_version", "dta_create", "dta_destroy", "dta_last_error", "dta_set_option", "dta_get_option",
-           "dta_profile_read", "dta_query_sizes", "dta_forward", "dta_backward"]
+           "dta_profile_read", "dta_query_sizes", "dta_forward", "dta_backward", "dta_loss_workspace_bytes",
+           "dta_cross_entropy_heads"]
 
 
 def sources():
@@ -129,6 +130,11 @@ def lib():
                                    C.POINTER(C.c_void_p * 6), C.c_void_p, C.POINTER(Tensors), C.c_void_p,
                                    C.c_void_p, C.c_void_p]
         L.dta_backward.restype = C.c_int
+        L.dta_loss_workspace_bytes.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t)]
+        L.dta_loss_workspace_bytes.restype = C.c_int
+        L.dta_cross_entropy_heads.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p * 8), C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p * 8), C.c_void_p, C.c_void_p]
+        L.dta_cross_entropy_heads.restype = C.c_int
         _lib = L
         return L
 

@@ -9,6 +9,7 @@
 #include "dta_common.cuh"
 #include "dta_conv_simt.cuh"
 #include "dta_conv_tc.cuh"
+#include "dta_loss.cuh"
 #include "dta_misc.cuh"
 
 using namespace dta;
@@ -722,6 +723,43 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("forward: ") + cudaGetErrorString(e));
+  return DTA_OK;
+}
+
+int dta_loss_workspace_bytes(int batch, int n_heads, size_t* out) {
+  if (!out || batch <= 0 || n_heads <= 0 || n_heads > 7) return DTA_ERR_INVALID_ARG;
+  *out = 256 + (size_t)n_heads * batch * sizeof(float);
+  return DTA_OK;
+}
+
+int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, const float* const scores[], const int64_t* labels,
+                            const float* class_weight, float* loss, float* const dscores[], void* workspace, void* cuda_stream) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  if (batch <= 0 || classes <= 0 || n_heads <= 0 || n_heads > 7) return fail(ctx, DTA_ERR_INVALID_ARG, "batch, classes must be positive and 1 <= n_heads <= 7");
+  if (!scores || !labels || !loss || !workspace) return fail(ctx, DTA_ERR_INVALID_ARG, "scores, labels, loss and workspace are required");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
+  cudaGetLastError();
+  ctx->launches = 0;
+  HeadPtrs h{};
+  for (int i = 0; i < n_heads; ++i) {
+    if (!scores[i]) return fail(ctx, DTA_ERR_INVALID_ARG, "scores[i] is NULL");
+    h.s[i] = scores[i];
+    h.ds[i] = dscores ? dscores[i] : nullptr;
+  }
+  double* den = static_cast<double*>(workspace);
+  int* bad = reinterpret_cast<int*>(static_cast<char*>(workspace) + 64);
+  float* rows = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
+  StageScope sc(ctx, "loss.cross_entropy", st);
+  cudaMemsetAsync(bad, 0, sizeof(int), st);
+  ce_den_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const long long*>(labels), class_weight, batch, classes, den, bad);
+  DTA_CHECK_LAUNCH(ctx, "ce_den");
+  const long long warps = (long long)n_heads * batch;
+  ce_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(h, n_heads, reinterpret_cast<const long long*>(labels), class_weight, batch,
+                                                                     classes, den, rows);
+  DTA_CHECK_LAUNCH(ctx, "ce_rows");
+  ce_finish_kernel<<<1, 256, 0, st>>>(rows, n_heads, batch, den, loss);
+  DTA_CHECK_LAUNCH(ctx, "ce_finish");
   return DTA_OK;
 }
 

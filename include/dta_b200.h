@@ -167,6 +167,23 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
                  const void* saved, const float* const dscores[6], const float* djoint,
                  const dta_tensors* grads, float* dx, void* workspace, void* cuda_stream);
 
+/*
+ * Weighted cross-entropy over n_heads (<= 7) score tensors and its gradient, in one pass.
+ * Replaces  F.cross_entropy(y_hat, y, weight=self.loss_weight)  of TreeModel.training_step /
+ * validation_step (src/main.py:78,89; weights :66-69), summed over the heads handed in (the
+ * reference's regime is n_heads = 1 with the joint scores).
+ *   scores[i] : (batch, classes) float32        labels : (batch) int64, 0 <= y < classes
+ *   class_weight : (classes) float32 or NULL (= ones, what the reference uses on a CPU host)
+ *   loss      : n_heads + 1 floats: per-head  sum_b w[y_b] nll_b / sum_b w[y_b], then their sum
+ *   dscores[i]: (batch, classes) d(sum of head losses)/d(scores[i]); dscores or entries may be NULL
+ *   workspace : dta_loss_workspace_bytes(batch, n_heads) bytes
+ * Labels outside [0, classes) contribute nothing (PyTorch raises; check on the host if needed).
+ */
+int dta_loss_workspace_bytes(int batch, int n_heads, size_t* out);
+int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, const float* const scores[],
+                            const int64_t* labels, const float* class_weight, float* loss,
+                            float* const dscores[], void* workspace, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,3 +170,53 @@ def test_cpu_input_raises():
         m(torch.randn(2, 3, 11, 11))
     with pytest.raises(ValueError):
         m(torch.randn(2, 4, 11, 11).cuda())
+
+
+@pytest.mark.parametrize("n_heads,classes,batch,weighted", [(1, 50, 64, True), (6, 50, 33, False), (3, 7, 5, True)])
+def test_fused_cross_entropy_matches_torch(n_heads, classes, batch, weighted):
+    """dta_cross_entropy_heads vs F.cross_entropy(weight=...) summed over heads (src/main.py:78): loss 1e-6
+    relative, score gradients 1e-7 absolute."""
+    from deeptreeattention_b200.loss import cross_entropy_heads
+    g = torch.Generator().manual_seed(5)
+    heads = [torch.randn(batch, classes, generator=g) * 3 for _ in range(n_heads)]
+    y = torch.randint(0, classes, (batch,), generator=g)
+    w = torch.rand(classes, generator=g) + 0.1 if weighted else None
+    ref_in = [h.clone().double().requires_grad_(True) for h in heads]
+    ref = sum(torch.nn.functional.cross_entropy(h, y, weight=w.double() if w is not None else None) for h in ref_in)
+    ref.backward()
+    dev_in = [h.cuda().requires_grad_(True) for h in heads]
+    loss = cross_entropy_heads(dev_in, y.cuda(), w.cuda() if w is not None else None)
+    (2.0 * loss).backward()
+    assert abs(float(loss) - float(ref)) <= 2e-6 * max(1.0, abs(float(ref)))
+    for a, b in zip(dev_in, ref_in):
+        np.testing.assert_allclose(a.grad.cpu().numpy(), 2.0 * b.grad.float().numpy(), rtol=1e-5, atol=2e-7)
+
+
+def test_graphed_step_equals_eager_step():
+    """A CUDA-graph replay of forward + fused loss + backward leaves the same loss and gradients as eager launches."""
+    from deeptreeattention_b200 import Hang2020 as H
+    from deeptreeattention_b200.graph import GraphedTrainStep
+    from deeptreeattention_b200.loss import cross_entropy_heads
+    table = orc.init_params("hang2020", 40, 6, 11, perturb_bn=True)
+    x, y = orc.make_inputs(12, 40, 6, 11)
+    x2, y2 = orc.make_inputs(12, 40, 6, 12)
+
+    def loss_fn(m, out, yy):
+        return cross_entropy_heads(m.head_scores + [out], yy)
+
+    def fresh():
+        m = H.Hang2020(40, 6)
+        m.load_state_dict(table)
+        return m.cuda().train()
+
+    me = fresh()
+    loss_e = loss_fn(me, me(x2.cuda()), y2.cuda())
+    loss_e.backward()
+    mg = fresh()
+    step = GraphedTrainStep(mg, x.cuda(), y.cuda(), loss_fn, warmup=1)
+    loss_g = step(x2.cuda(), y2.cuda())
+    torch.cuda.synchronize()
+    assert float(loss_g) == float(loss_e)
+    for (k, pe), (_, pg) in zip(me.named_parameters(), mg.named_parameters()):
+        assert pg.grad is not None, k
+        assert torch.equal(pe.grad, pg.grad), k
