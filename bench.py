@@ -342,9 +342,18 @@ def run_b200(args):
     barrier()
     e2e_value = world * B * args.steps / t_e2e
 
-    if rank != 0:
+    def finish():
+        """Leave without tearing NCCL down: destroying the communicator while captured graphs that hold NCCL kernels are
+        alive can block forever; every rank has finished its work by the barrier, so a hard exit is safe."""
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     # ---- roofline ---------------------------------------------------------------------------
@@ -408,8 +417,7 @@ def run_b200(args):
         "gpu_launches": launches,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():

@@ -163,7 +163,11 @@ struct FwdWork {
 FwdWork layout_fwd(const dta_shape& s, const NetDesc& d, void* base) {
   FwdWork W{};
   Carver c(base);
-  W.stats = c.take((size_t)s.batch * d.nb * 128 * 2);
+  {
+    size_t n = (size_t)s.batch * d.nb * 128 * 2;                       // SIMT path: one row per CTA (<= batch)
+    const size_t n_tc = (size_t)kTcSmCount * 4 * d.nb * 128 * 2;      // tensor-core path: four rows per persistent CTA
+    W.stats = c.take(n > n_tc ? n : n_tc);
+  }
   W.wpf[0] = take_bf16(c, (size_t)tc_geom(s.batch, s.bands, d.nb).nstage1 * (TcFprop<11, 64, false>::W_BYTES / 16));
   W.wpf[1] = take_bf16(c, (size_t)d.nb * 2 * (TcFprop<11, 64, false>::W_BYTES / 16));
   W.wpf[2] = take_bf16(c, (size_t)d.nb * 4 * (TcFprop<5, 128, true>::W_BYTES / 16));
@@ -185,6 +189,16 @@ Splits wgrad_splits(int B) {
   return sp;
 }
 
+// Upper bound of the 32x32 tiles the batched small-gradient reduction needs (sizes the partial buffer).
+int reduce_tiles_bound(int classes, int nb) {
+  const int ct = (classes + 31) / 32;
+  // per branch: heads (F <= 512 -> 16 tiles along j, three heads: 4 + 8 + 16), their biases, spectral CxC (1 + 4 + 16) x 2, ~30 column sums
+  int per_branch = ct * (4 + 8 + 16) + 3 * ct + 2 * (1 + 4 + 16) + 40;
+  const int vanilla = ct * 16 + ct;
+  if (vanilla > per_branch) per_branch = vanilla;
+  return nb * per_branch;
+}
+
 struct BwdWork {
   float* dS[6];
   float* da[3];
@@ -196,6 +210,7 @@ struct BwdWork {
   float* wd[3];
   __nv_bfloat16* dzp;      // split-bf16 position stream of the current block's conv-output gradient
   __nv_bfloat16* wdp[2];   // packed input-gradient weights of conv2, conv3 (tensor-core path)
+  float* rpart;            // partial tiles of the batched small-gradient reduction
   size_t bytes;
 };
 BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
@@ -226,6 +241,7 @@ BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
   W.dzp = take_bf16(c, dz16);
   W.wdp[0] = take_bf16(c, (size_t)d.nb * 4 * (TcFprop<11, 32, true>::W_BYTES / 16));
   W.wdp[1] = take_bf16(c, (size_t)d.nb * 8 * (TcFprop<5, 64, true>::W_BYTES / 16));
+  W.rpart = c.take((size_t)reduce_tiles_bound(s.classes, d.nb) * kReduceSplits * 1024);
   W.wd[0] = c.take((size_t)d.nb * 32 * 9 * s.bands);
   W.wd[1] = c.take((size_t)d.nb * 64 * 9 * 32);
   W.wd[2] = c.take((size_t)d.nb * 128 * 9 * 64);
@@ -341,7 +357,7 @@ cudaError_t launch_wgrad(const ConvSrc& in, const ConvSrc& dz, float* part, int 
 template <int S, int NCO, bool ACC2>
 cudaError_t run_tc_fprop(dta_ctx* ctx, cudaStream_t st, const __nv_bfloat16* xp, size_t rows, int nchunk, int chunks_per_group,
                          const __nv_bfloat16* wp, int nstage, Ptr2 bias, int bias_split, float* out, int out_ctot, int cout_g, int B,
-                         int G) {
+                         int G, float* stats = nullptr, int* nblk = nullptr) {
   using Cfg = TcFprop<S, NCO, ACC2>;
   auto kern = tc_conv_fprop_kernel<S, NCO, ACC2>;
   cudaError_t e = allow_smem(kern, Cfg::SMEM_BYTES);
@@ -349,8 +365,9 @@ cudaError_t run_tc_fprop(dta_ctx* ctx, cudaStream_t st, const __nv_bfloat16* xp,
   const int ntiles = (int)((rows - 2 * kTcGuard) / Cfg::TILE);
   const int nwork = ntiles * G;
   const int grid = nwork < ctx->sm_count ? nwork : ctx->sm_count;
+  if (nblk) *nblk = grid * 4;
   kern<<<grid, kTcFpropThreads, Cfg::SMEM_BYTES, st>>>(xp, rows, nchunk, chunks_per_group, wp, nstage, bias, bias_split, out, out_ctot, cout_g,
-                                                  B, ntiles, G);
+                                                       B, ntiles, G, stats);
   return cudaGetLastError();
 }
 template <int S, class Cfg>
@@ -365,7 +382,14 @@ cudaError_t run_tc_wgrad(cudaStream_t st, const __nv_bfloat16* dzp, int dz_chunk
 }
 template <int S>
 cudaError_t run_tc_pack(dta_ctx* ctx, cudaStream_t st, const ConvSrc& src, int G, int B, int nchunk, size_t rows, __nv_bfloat16* dst) {
-  tc_pack_stream_kernel<S><<<ctx->sm_count * 8, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
+  const size_t total = rows * nchunk;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
+  const int grid = (int)blocks;
+  if (src.mode == SRC_RAW) tc_pack_stream_kernel<S, SRC_RAW, false><<<grid, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
+  else if (src.mode == SRC_DZ) tc_pack_stream_kernel<S, SRC_DZ, false><<<grid, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
+  else if (src.pool) tc_pack_stream_kernel<S, SRC_ACT, true><<<grid, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
+  else tc_pack_stream_kernel<S, SRC_ACT, false><<<grid, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
   return cudaGetLastError();
 }
 int run_bn_stats(dta_ctx* ctx, cudaStream_t st, const float* z, int B, int ctot, int hw, float* stats) {
@@ -601,13 +625,9 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     }
     {
       StageScope sc(ctx, "fwd.conv1", st);
-      DTA_TC_CHECK((run_tc_fprop<11, 64, false>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32, nb * 32, B, 1)),
+      DTA_TC_CHECK((run_tc_fprop<11, 64, false>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32, nb * 32, B, 1,
+                                               shape->training ? W.stats : nullptr, &nblk)),
                    "tc_conv_fprop(conv1)");
-    }
-    if (shape->training) {
-      StageScope sc(ctx, "fwd.bn_stats", st);
-      nblk = run_bn_stats(ctx, st, L.z[0], B, nb * 32, kHW, W.stats);
-      DTA_CHECK_LAUNCH(ctx, "bn_partial_stats");
     }
   } else {
     StageScope sc(ctx, "fwd.conv1", st);
@@ -622,7 +642,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   auto bn_finalize = [&](int k, int nblk_k) -> int {
     StageScope sc(ctx, "fwd.bn_finalize", st);
     const int ctot = nb * kC[k];
-    bn_fwd_finalize_kernel<<<(ctot * 32 + 255) / 256, 256, 0, st>>>(W.stats, nblk_k, ctot, (double)B * kHWpre[k], bn_params(params, d, k),
+    bn_fwd_finalize_kernel<<<(ctot + 31) / 32, 32 * kBnSlices, 0, st>>>(W.stats, nblk_k, ctot, (double)B * kHWpre[k], bn_params(params, d, k),
                                                                     shape->training, L.bn_mean[k], L.bn_istd[k], L.bn_scale[k], L.bn_shift[k]);
     DTA_CHECK_LAUNCH(ctx, "bn_fwd_finalize");
     return DTA_OK;
@@ -653,12 +673,8 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     }
     {
       StageScope sc(ctx, "fwd.conv2", st);
-      DTA_TC_CHECK((run_tc_fprop<11, 64, true>(ctx, st, L.a1p, tg.rows11, nb * 4, 4, W.wpf[1], 2, conv_b(1), 64, L.z[1], nb * 64, 64, B, nb)), "tc_conv_fprop(conv2)");
-    }
-    if (shape->training) {
-      StageScope sc(ctx, "fwd.bn_stats", st);
-      nblk = run_bn_stats(ctx, st, L.z[1], B, nb * 64, kHW, W.stats);
-      DTA_CHECK_LAUNCH(ctx, "bn_partial_stats");
+      DTA_TC_CHECK((run_tc_fprop<11, 64, true>(ctx, st, L.a1p, tg.rows11, nb * 4, 4, W.wpf[1], 2, conv_b(1), 64, L.z[1], nb * 64, 64, B, nb,
+                                              shape->training ? W.stats : nullptr, &nblk)), "tc_conv_fprop(conv2)");
     }
   } else {
     StageScope sc(ctx, "fwd.conv2", st);
@@ -688,12 +704,8 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     }
     {
       StageScope sc(ctx, "fwd.conv3", st);
-      DTA_TC_CHECK((run_tc_fprop<5, 128, true>(ctx, st, L.a2p, tg.rows5, nb * 8, 8, W.wpf[2], 4, conv_b(2), 128, L.z[2], nb * 128, 128, B, nb)), "tc_conv_fprop(conv3)");
-    }
-    if (shape->training) {
-      StageScope sc(ctx, "fwd.bn_stats", st);
-      nblk = run_bn_stats(ctx, st, L.z[2], B, nb * 128, 25, W.stats);
-      DTA_CHECK_LAUNCH(ctx, "bn_partial_stats");
+      DTA_TC_CHECK((run_tc_fprop<5, 128, true>(ctx, st, L.a2p, tg.rows5, nb * 8, 8, W.wpf[2], 4, conv_b(2), 128, L.z[2], nb * 128, 128, B, nb,
+                                              shape->training ? W.stats : nullptr, &nblk)), "tc_conv_fprop(conv3)");
     }
   } else {
     StageScope sc(ctx, "fwd.conv3", st);
@@ -861,7 +873,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   auto bn_bwd = [&](int k) -> int {
     StageScope sc(ctx, "bwd.bn_finalize", st);
     const int ctot = nb * kC[k];
-    bn_bwd_finalize_kernel<<<(ctot * 32 + 255) / 256, 256, 0, st>>>(W.bnrows, B, nb, kC[k], (double)B * kHWpre[k], bn_params(params, d, k),
+    bn_bwd_finalize_kernel<<<(ctot + 31) / 32, 32 * kBnSlices, 0, st>>>(W.bnrows, B, nb, kC[k], (double)B * kHWpre[k], bn_params(params, d, k),
                                                                     L.bn_mean[k], L.bn_istd[k], shape->training, bn_grads(k), W.k0[k], W.k1[k], W.k2[k]);
     DTA_CHECK_LAUNCH(ctx, "bn_bwd_finalize");
     return DTA_OK;
@@ -1033,8 +1045,11 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   }
   if (rtiles > 0) {
     StageScope sc(ctx, "bwd.small_param_grads", st);
-    batched_reduce_kernel<<<rtiles, 256, 0, st>>>(rtab, B);
+    if (rtiles > reduce_tiles_bound(classes, nb)) return fail(ctx, DTA_ERR_UNSUPPORTED, "reduction tile bound exceeded");
+    batched_reduce_kernel<<<dim3(rtiles, kReduceSplits), 256, 0, st>>>(rtab, B, W.rpart);
     DTA_CHECK_LAUNCH(ctx, "batched_reduce");
+    batched_reduce_finish_kernel<<<rtiles, 256, 0, st>>>(rtab, W.rpart);
+    DTA_CHECK_LAUNCH(ctx, "batched_reduce_finish");
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("backward: ") + cudaGetErrorString(e));

@@ -7,7 +7,7 @@
 
 namespace dta {
 
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;
 
 // Per-branch parameter views used by the attention kernels (device pointers).
 struct AttnParams {

@@ -51,12 +51,14 @@ inline size_t tc_rows(int B, int pc, int tile) {
 // =======================================================================================
 // Packing kernels (HBM-bound elementwise; one thread = 8 channels x 1 stream position)
 // =======================================================================================
-// Crops / activations -> split-bf16 position stream.  src is produced by conv_src_load, so the
-// same kernel packs raw crops (SRC_RAW), gated activations (SRC_ACT) and BatchNorm-backward
-// gradients (SRC_DZ).  Channels >= cin_total, pad positions and guard rows are written as zeros.
-//   dst[half][chunk][rows][8],  chunk = channel / 8 over the concatenated groups
-template <int S>
-__global__ void tc_pack_stream_kernel(ConvSrc src, int G, int B, int nchunk, size_t rows, __nv_bfloat16* __restrict__ dst) {
+// fp32 source -> split-bf16 position stream, dst[half][chunk][rows][8] (chunk = channel / 8 over the concatenated
+// groups).  One thread = 8 channels x 1 stream position; all loads of a thread are issued before any use (the kernels
+// are latency-bound otherwise).  Channels >= ctot, pad positions and guard rows are written as zeros.
+//   MODE SRC_RAW: the crops.   SRC_ACT: relu(z*scale+shift) [2x2 max-pooled] * attention gate.
+//   SRC_DZ: BatchNorm backward on the fly, k0*da + k1*z + k2.
+template <int S, int MODE, bool POOL>
+__global__ void __launch_bounds__(256)
+tc_pack_stream_kernel(ConvSrc src, int G, int B, int nchunk, size_t rows, __nv_bfloat16* __restrict__ dst) {
   using St = Stream<S>;
   const size_t total = rows * nchunk;
   const int ctot = G * src.cin;
@@ -67,18 +69,62 @@ __global__ void tc_pack_stream_kernel(ConvSrc src, int G, int B, int nchunk, siz
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
     const long long q = (long long)row - kTcGuard;
-    if (q >= 0 && q < (long long)B * St::PC) {
+    const int ch0 = chunk * 8;
+    if (q >= 0 && q < (long long)B * St::PC && ch0 < ctot) {
       const int b = (int)(q / St::PC);
       const int r = (int)(q - (long long)b * St::PC);
       const int yy = r / St::PT, xx = r - yy * St::PT;
       if (yy >= 1 && xx < S) {
-        const int p = (yy - 1) * S + xx;
+        const int y = yy - 1, p = y * S + xx;
+        const int nv = min(8, ctot - ch0);                  // live channels of this chunk
+        if (MODE == SRC_RAW) {
+          const float* a = src.a + ((size_t)b * src.ctot + ch0) * src.src_hw + p;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int ch = chunk * 8 + j;
-          if (ch < ctot) {
-            const int g = ch / src.cin;
-            v[j] = conv_src_load<S>(src, b, g, G, ch - g * src.cin, p);
+          for (int j = 0; j < 8; ++j)
+            if (j < nv) v[j] = __ldg(a + (size_t)j * src.src_hw);
+        } else if (MODE == SRC_DZ) {
+          const size_t base = ((size_t)b * src.ctot + ch0) * src.src_hw + p;
+          float da[8], zz[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { da[j] = __ldg(src.a + base + (size_t)j * src.src_hw); zz[j] = __ldg(src.b + base + (size_t)j * src.src_hw); }
+          const float4 k0a = __ldg(reinterpret_cast<const float4*>(src.k0 + ch0)), k0b = __ldg(reinterpret_cast<const float4*>(src.k0 + ch0) + 1);
+          const float4 k1a = __ldg(reinterpret_cast<const float4*>(src.k1 + ch0)), k1b = __ldg(reinterpret_cast<const float4*>(src.k1 + ch0) + 1);
+          const float4 k2a = __ldg(reinterpret_cast<const float4*>(src.k2 + ch0)), k2b = __ldg(reinterpret_cast<const float4*>(src.k2 + ch0) + 1);
+          const float k0[8] = {k0a.x, k0a.y, k0a.z, k0a.w, k0b.x, k0b.y, k0b.z, k0b.w};
+          const float k1[8] = {k1a.x, k1a.y, k1a.z, k1a.w, k1b.x, k1b.y, k1b.z, k1b.w};
+          const float k2[8] = {k2a.x, k2a.y, k2a.z, k2a.w, k2b.x, k2b.y, k2b.z, k2b.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = k0[j] * da[j] + k1[j] * zz[j] + k2[j];   // same association as conv_src_load
+        } else {
+          constexpr int SP = POOL ? 2 * S + 1 : S;          // side of the source plane
+          const int g = ch0 / src.cin;                       // cin is a multiple of 8 for activations
+          const float* zp = src.a + ((size_t)b * src.ctot + ch0) * src.src_hw + (POOL ? (2 * y) * SP + 2 * xx : p);
+          float z0[8], z1[8], z2[8], z3[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float* zj = zp + (size_t)j * src.src_hw;
+            z0[j] = __ldg(zj);
+            if (POOL) { z1[j] = __ldg(zj + 1); z2[j] = __ldg(zj + SP); z3[j] = __ldg(zj + SP + 1); }
+          }
+          const float4 sca = __ldg(reinterpret_cast<const float4*>(src.k0 + ch0)), scb = __ldg(reinterpret_cast<const float4*>(src.k0 + ch0) + 1);
+          const float4 sha = __ldg(reinterpret_cast<const float4*>(src.k1 + ch0)), shb = __ldg(reinterpret_cast<const float4*>(src.k1 + ch0) + 1);
+          const float sc[8] = {sca.x, sca.y, sca.z, sca.w, scb.x, scb.y, scb.z, scb.w};
+          const float sh[8] = {sha.x, sha.y, sha.z, sha.w, shb.x, shb.y, shb.z, shb.w};
+          const int gm = src.gate_mode[g];
+          const float* grow = src.gate + ((size_t)b * G + g) * src.gate_ld + src.gate_off;
+          float gate_p = 1.f;
+          if (gm == BR_SPATIAL) gate_p = __ldg(grow + p);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a = fmaxf(fmaf(z0[j], sc[j], sh[j]), 0.f);
+            if (POOL) {
+              const float a1 = fmaxf(fmaf(z1[j], sc[j], sh[j]), 0.f), a2 = fmaxf(fmaf(z2[j], sc[j], sh[j]), 0.f),
+                          a3 = fmaxf(fmaf(z3[j], sc[j], sh[j]), 0.f);
+              a = fmaxf(fmaxf(a, a1), fmaxf(a2, a3));
+            }
+            float gv = gate_p;
+            if (gm == BR_SPECTRAL) gv = __ldg(grow + (ch0 - g * src.cin) + j);
+            v[j] = (gm == BR_NONE) ? a : a * gv;
           }
         }
       }
@@ -164,7 +210,8 @@ template <int S, int NCO, bool ACC2>
 __global__ void __launch_bounds__(kTcFpropThreads, 1)
 tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]*/, size_t rows, int nchunk, int chunks_per_group,
                      const __nv_bfloat16* __restrict__ wp /*[G][nstage][W_BYTES]*/, int nstage, Ptr2 bias, int bias_split,
-                     float* __restrict__ out /*[B][out_ctot][S*S]*/, int out_ctot, int cout_g, int B, int ntiles, int G) {
+                     float* __restrict__ out /*[B][out_ctot][S*S]*/, int out_ctot, int cout_g, int B, int ntiles, int G,
+                     float* __restrict__ stats /*[gridDim.x*4][out_ctot][2] or null: BatchNorm partial sums of out*/) {
   using Cfg = TcFprop<S, NCO, ACC2>;
   using St = Stream<S>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -263,6 +310,12 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
     const int chalf = ew >> 2;                 // which half of the output channels
     const int et = tid - 64;                   // 0..255
     constexpr int CH_PER = NCO / 2;
+    constexpr int NGRP = (CH_PER + 31) / 32;   // 32-channel groups per thread (lane l ends up owning channel 32*grp + l)
+    float run_sum[2][NGRP], run_sq[2][NGRP];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < NGRP; ++c) { run_sum[a][c] = 0.f; run_sq[a][c] = 0.f; }
     uint32_t tile_it = 0;
     for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++tile_it) {
       const int g = work / ntiles, tile = work - g * ntiles;
@@ -277,33 +330,88 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
       asm volatile("bar.sync 1, 256;" : : : "memory");
       tc::mbar_wait(&tmem_full[acc], acc_use & 1);
       tc::fence_after_sync();
+#pragma unroll
+      for (int grp = 0; grp < NGRP; ++grp) {
+        constexpr int GW = CH_PER < 32 ? CH_PER : 32;        // channels in this group
+        float ps[GW], pq[GW];                                 // this thread's sums over its positions of the tile
+#pragma unroll
+        for (int j = 0; j < GW; ++j) { ps[j] = 0.f; pq[j] = 0.f; }
+        const int cg0 = chalf * CH_PER + grp * 32;
 #pragma unroll 1
-      for (int s = 0; s < Cfg::SUB; ++s) {
-        const long long q = (long long)tile * Cfg::TILE + s * 128 + quad * 32 + lane;
-        const int b = (int)(q / St::PC);
-        const int r = (int)(q - (long long)b * St::PC);
-        const int yy = r / St::PT, xx = r - yy * St::PT;
-        const bool valid = b < B && yy >= 1 && xx < S;
-        float* orow = out + ((size_t)b * out_ctot + (size_t)g * cout_g) * (S * S) + (yy - 1) * S + xx;
-        const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * Cfg::ACC_COLS + s * (2 * NCO);
+        for (int s = 0; s < Cfg::SUB; ++s) {
+          const long long q = (long long)tile * Cfg::TILE + s * 128 + quad * 32 + lane;
+          const int b = (int)(q / St::PC);
+          const int r = (int)(q - (long long)b * St::PC);
+          const int yy = r / St::PT, xx = r - yy * St::PT;
+          const bool valid = b < B && yy >= 1 && xx < S;
+          float* orow = out + ((size_t)b * out_ctot + (size_t)g * cout_g) * (S * S) + (yy - 1) * S + xx;
+          const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * Cfg::ACC_COLS + s * (2 * NCO);
 #pragma unroll
-        for (int cc = 0; cc < CH_PER; cc += 16) {
-          const int c0 = chalf * CH_PER + cc;
-          if (c0 < cout_g) {
-            float v0[16], v1[16];
-            tc::tmem_ld16(taddr + c0, v0);
-            tc::tmem_ld16(taddr + NCO + c0, v1);
-            tc::tmem_ld_wait();
-            if (valid) {
+          for (int cc = 0; cc < GW; cc += 16) {
+            const int c0 = cg0 + cc;
+            if (c0 < cout_g) {
+              float v0[16], v1[16];
+              tc::tmem_ld16(taddr + c0, v0);
+              tc::tmem_ld16(taddr + NCO + c0, v1);
+              tc::tmem_ld_wait();
+              if (valid) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) orow[(size_t)(c0 + j) * (S * S)] = v0[j] + v1[j] + sb[c0 + j];
+                for (int j = 0; j < 16; ++j) {
+                  const float o = v0[j] + v1[j] + sb[c0 + j];
+                  orow[(size_t)(c0 + j) * (S * S)] = o;
+                  ps[cc + j] += o;
+                  pq[cc + j] = fmaf(o, o, pq[cc + j]);
+                }
+              }
             }
           }
+        }
+        if (stats != nullptr) {
+          // halving butterfly: after log2(32) rounds lane l holds the warp total of channel cg0 + (l % GW)
+          float rs = 0.f, rq = 0.f;
+          if (GW == 32) {
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+              const bool upper = (lane & w) != 0;
+#pragma unroll
+              for (int j = 0; j < w; ++j) {
+                const float keep_s = upper ? ps[j + w] : ps[j], send_s = upper ? ps[j] : ps[j + w];
+                const float keep_q = upper ? pq[j + w] : pq[j], send_q = upper ? pq[j] : pq[j + w];
+                ps[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+                pq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+              }
+            }
+            rs = ps[0]; rq = pq[0];
+          } else {   // GW == 16: plain xor-reduce of 16 values, lane l reports channel l % 16
+#pragma unroll
+            for (int j = 0; j < GW; ++j) {
+              float a = ps[j], c = pq[j];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+              if ((lane % GW) == j) { rs = a; rq = c; }
+            }
+          }
+          run_sum[g & 1][grp] += rs;
+          run_sq[g & 1][grp] += rq;
         }
       }
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+    }
+    if (stats != nullptr) {
+      // partial statistics of this warp's positions: row (cta*4 + quad), channel (g*cout_g + chalf*CH_PER + 32*grp + lane)
+      constexpr int GW = CH_PER < 32 ? CH_PER : 32;
+      float* srow = stats + ((size_t)blockIdx.x * 4 + quad) * out_ctot * 2;
+      for (int g = 0; g < G && g < 2; ++g)
+#pragma unroll
+        for (int grp = 0; grp < NGRP; ++grp) {
+          const int ch = chalf * CH_PER + grp * 32 + lane;
+          if (lane < GW && ch < cout_g) {
+            srow[(size_t)(g * cout_g + ch) * 2 + 0] = run_sum[g][grp];
+            srow[(size_t)(g * cout_g + ch) * 2 + 1] = run_sq[g][grp];
+          }
+        }
     }
   }
   tc::fence_before_sync();

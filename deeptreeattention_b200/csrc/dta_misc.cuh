@@ -65,46 +65,55 @@ struct BnParams {
   int c_per_branch;
 };
 
-// One warp per channel.  training: reduce the conv kernels' per-CTA partial sums in fp64,
-// produce mean / invstd / scale / shift and update the running statistics (momentum 0.1,
-// unbiased variance) exactly like nn.BatchNorm2d in train(); eval: use running statistics.
-__global__ void bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int nblk, int ctot,
-                                       double count, BnParams bn, int training, float* __restrict__ mean,
-                                       float* __restrict__ istd, float* __restrict__ scale, float* __restrict__ shift) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= ctot) return;
-  const int br = warp / bn.c_per_branch, c = warp - br * bn.c_per_branch;
+constexpr int kBnSlices = 32;   // row slices per block in the BatchNorm finalize kernels (block = 32 channels x 32 slices)
+
+// Block = 32 channels x 32 row slices (coalesced 128-byte reads), fp64 accumulation in fixed order.
+// training: reduce the conv kernels' partial sums, produce mean / invstd / scale / shift and update the running
+// statistics (momentum 0.1, unbiased variance) exactly like nn.BatchNorm2d in train(); eval: use running statistics.
+__global__ void __launch_bounds__(32 * kBnSlices)
+bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int nblk, int ctot, double count, BnParams bn,
+                       int training, float* __restrict__ mean, float* __restrict__ istd, float* __restrict__ scale,
+                       float* __restrict__ shift) {
+  __shared__ double ss[kBnSlices][33], sq[kBnSlices][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cx;
+  double s = 0.0, q = 0.0;
+  if (training && ch < ctot) {
+#pragma unroll 4
+    for (int k = ry; k < nblk; k += kBnSlices) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(part + ((size_t)k * ctot + ch) * 2));
+      s += (double)v.x;
+      q += (double)v.y;
+    }
+  }
+  ss[ry][cx] = s;
+  sq[ry][cx] = q;
+  __syncthreads();
+  if (ry != 0 || ch >= ctot) return;
+  s = 0.0; q = 0.0;
+#pragma unroll
+  for (int k = 0; k < kBnSlices; ++k) { s += ss[k][cx]; q += sq[k][cx]; }
+  const int br = ch / bn.c_per_branch, c = ch - br * bn.c_per_branch;
   float m, is;
   if (training) {
-    double s = 0.0, q = 0.0;
-    for (int k = lane; k < nblk; k += 32) {
-      s += (double)part[((size_t)k * ctot + warp) * 2 + 0];
-      q += (double)part[((size_t)k * ctot + warp) * 2 + 1];
-    }
-    s = warp_sum(s);
-    q = warp_sum(q);
     const double mu = s / count;
     double var = q / count - mu * mu;
     if (var < 0.0) var = 0.0;
     m = (float)mu;
     is = (float)(1.0 / sqrt(var + (double)kBnEps));
-    if (lane == 0) {
-      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      bn.rm[br][c] = (float)((1.0 - kBnMomentum) * (double)bn.rm[br][c] + kBnMomentum * mu);
-      bn.rv[br][c] = (float)((1.0 - kBnMomentum) * (double)bn.rv[br][c] + kBnMomentum * unbiased);
-      if (c == 0 && bn.nbt[br] != nullptr) bn.nbt[br][0] += 1;
-    }
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    bn.rm[br][c] = (float)((1.0 - kBnMomentum) * (double)bn.rm[br][c] + kBnMomentum * mu);
+    bn.rv[br][c] = (float)((1.0 - kBnMomentum) * (double)bn.rv[br][c] + kBnMomentum * unbiased);
+    if (c == 0 && bn.nbt[br] != nullptr) bn.nbt[br][0] += 1;
   } else {
     m = bn.rm[br][c];
     is = (float)(1.0 / sqrt((double)bn.rv[br][c] + (double)kBnEps));
   }
-  if (lane == 0) {
-    const float sc = bn.gamma[br][c] * is;
-    mean[warp] = m;
-    istd[warp] = is;
-    scale[warp] = sc;
-    shift[warp] = bn.beta[br][c] - m * sc;
-  }
+  const float sc = bn.gamma[br][c] * is;
+  mean[ch] = m;
+  istd[ch] = is;
+  scale[ch] = sc;
+  shift[ch] = bn.beta[br][c] - m * sc;
 }
 
 struct BnGrads {
@@ -113,30 +122,38 @@ struct BnGrads {
   float* dconv_b[2];
 };
 
-// One warp per channel.  rows[b][ctot*2] hold per-crop (sum da | sum da*zhat); reduce over
-// the batch in fp64 (fixed order), emit dgamma / dbeta / dbias and the coefficients of
+// Block = 32 channels x 32 crop slices.  rows[b][g][2C] hold per-crop (sum da | sum da*zhat); reduce over the batch in
+// fp64 (fixed order), emit dgamma / dbeta / dbias and the coefficients of
 //   dz = k0*da + k1*z + k2     (train: k0 = gamma*istd, k1 = -k0*istd*dgamma/N,
 //                               k2 = -k0*dbeta/N - k1*mean;  eval: k1 = k2 = 0)
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, int G, int C, double count,
-                                       BnParams bn, const float* __restrict__ mean, const float* __restrict__ istd,
-                                       int training, BnGrads gr, float* __restrict__ k0, float* __restrict__ k1,
-                                       float* __restrict__ k2) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(32 * kBnSlices)
+bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, int G, int C, double count, BnParams bn, const float* __restrict__ mean,
+                       const float* __restrict__ istd, int training, BnGrads gr, float* __restrict__ k0, float* __restrict__ k1,
+                       float* __restrict__ k2) {
+  __shared__ double sa[kBnSlices][33], sb[kBnSlices][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int ctot = G * C;
-  if (warp >= ctot) return;
-  const int g = warp / C, c = warp - g * C;
+  const int ch = blockIdx.x * 32 + cx;
+  const int g = ch / C, c = ch - g * C;
   double s1 = 0.0, s2 = 0.0;
-  for (int b = lane; b < B; b += 32) {
-    const float* r = rows + ((size_t)b * G + g) * 2 * C;
-    s1 += (double)r[c];
-    s2 += (double)r[C + c];
+  if (ch < ctot) {
+#pragma unroll 4
+    for (int b = ry; b < B; b += kBnSlices) {
+      const float* r = rows + ((size_t)b * G + g) * 2 * C;
+      s1 += (double)__ldg(r + c);
+      s2 += (double)__ldg(r + C + c);
+    }
   }
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if (lane != 0) return;
-  const int br = warp / bn.c_per_branch, cb = warp - br * bn.c_per_branch;
+  sa[ry][cx] = s1;
+  sb[ry][cx] = s2;
+  __syncthreads();
+  if (ry != 0 || ch >= ctot) return;
+  s1 = 0.0; s2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < kBnSlices; ++k) { s1 += sa[k][cx]; s2 += sb[k][cx]; }
+  const int br = ch / bn.c_per_branch, cb = ch - br * bn.c_per_branch;
   const double gam = bn.gamma[br][cb];
-  const double is = istd[warp], mu = mean[warp];
+  const double is = istd[ch], mu = mean[ch];
   const double a = gam * is;
   double b1 = 0.0, b2 = 0.0, dbias;
   if (training) {
@@ -146,9 +163,9 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, in
   } else {
     dbias = a * s1;
   }
-  k0[warp] = (float)a;
-  k1[warp] = (float)b1;
-  k2[warp] = (float)b2;
+  k0[ch] = (float)a;
+  k1[ch] = (float)b1;
+  k2[ch] = (float)b2;
   if (gr.dgamma[br]) gr.dgamma[br][cb] = (float)s2;
   if (gr.dbeta[br]) gr.dbeta[br][cb] = (float)s1;
   if (gr.dconv_b[br]) gr.dconv_b[br][cb] = (float)dbias;
@@ -239,11 +256,11 @@ __global__ void alpha_grad_kernel(const float* __restrict__ djoint, const float*
 }
 
 // ---------------------------------------------------------------------------------------
-// All small parameter gradients of a backward pass in ONE launch.  Each task is a batch
-// reduction  out[i*si + j*sj] = sum_b U[b*ldu + i] * V[b*ldv + j]  (V == nullptr: column sums of
-// U, nj = 1): attention / classifier weight and bias gradients.  A CTA owns one 32x32 output
-// tile (outer products) or 32 columns (column sums) and walks the batch in fixed order, so
-// the result is deterministic.
+// All small parameter gradients of a backward pass in two launches.  Each task is a batch reduction
+//   out[i*si + j*sj] = sum_b U[b*ldu + i] * V[b*ldv + j]   (V == nullptr: column sums of U, nj = 1):
+// attention / classifier weight and bias gradients.  Stage 1: a CTA owns one 32x32 output tile (outer products) or
+// 32 columns (column sums) of one task for one of kReduceSplits slices of the batch and writes a partial tile;
+// stage 2 adds the slices in fixed order (deterministic, no atomics).
 // ---------------------------------------------------------------------------------------
 struct ReduceTask {
   const float* U;
@@ -251,16 +268,18 @@ struct ReduceTask {
   float* out;
   long long ldu, ldv, si, sj;
   int ni, nj;
-  int tile_begin;   // first CTA of this task
+  int tile_begin;   // first tile of this task
   int tiles_j;      // tiles along j
 };
 constexpr int kMaxReduceTasks = 96;
+constexpr int kReduceSplits = 8;
 struct ReduceTaskTable {
   ReduceTask t[kMaxReduceTasks];
   int n;
 };
 
-__global__ void __launch_bounds__(256) batched_reduce_kernel(const __grid_constant__ ReduceTaskTable tab, int B) {
+// grid = (tiles, kReduceSplits); partial[tile][split][32*32]
+__global__ void __launch_bounds__(256) batched_reduce_kernel(const __grid_constant__ ReduceTaskTable tab, int B, float* __restrict__ partial) {
   __shared__ float su[32][33];
   __shared__ float sv[32][33];
   int ti = 0;
@@ -268,32 +287,35 @@ __global__ void __launch_bounds__(256) batched_reduce_kernel(const __grid_consta
   const ReduceTask& T = tab.t[ti];
   const int tile = blockIdx.x - T.tile_begin;
   const int tid = threadIdx.x;
+  const int per = (B + kReduceSplits - 1) / kReduceSplits;
+  const int b_begin = blockIdx.y * per, b_end = min(B, b_begin + per);
+  float* pout = partial + ((size_t)blockIdx.x * kReduceSplits + blockIdx.y) * 1024;
   if (T.V == nullptr) {
     // column sums: 32 columns x 8 batch slices
     const int tx = tid & 31, ty = tid >> 5;
     const int j = tile * 32 + tx;
     float a = 0.f;
     if (j < T.ni)
-      for (int b = ty; b < B; b += 8) a += __ldg(T.U + (size_t)b * T.ldu + j);
+      for (int b = b_begin + ty; b < b_end; b += 8) a += __ldg(T.U + (size_t)b * T.ldu + j);
     su[ty][tx] = a;
     __syncthreads();
-    if (ty == 0 && j < T.ni) {
+    if (ty == 0) {
       float t = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) t += su[k][tx];
-      T.out[(size_t)j * T.si] = t;
+      pout[tx] = t;
     }
     return;
   }
   const int i0 = (tile / T.tiles_j) * 32, j0 = (tile % T.tiles_j) * 32;
   const int tx = tid & 15, ty = tid >> 4;   // each thread: outputs (2*ty + {0,1}, 2*tx + {0,1})
   float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-  for (int b0 = 0; b0 < B; b0 += 32) {
+  for (int b0 = b_begin; b0 < b_end; b0 += 32) {
     for (int e = tid; e < 32 * 32; e += 256) {
       const int bb = e >> 5, k = e & 31;
       const int b = b0 + bb;
-      su[bb][k] = (b < B && i0 + k < T.ni) ? __ldg(T.U + (size_t)b * T.ldu + i0 + k) : 0.f;
-      sv[bb][k] = (b < B && j0 + k < T.nj) ? __ldg(T.V + (size_t)b * T.ldv + j0 + k) : 0.f;
+      su[bb][k] = (b < b_end && i0 + k < T.ni) ? __ldg(T.U + (size_t)b * T.ldu + i0 + k) : 0.f;
+      sv[bb][k] = (b < b_end && j0 + k < T.nj) ? __ldg(T.V + (size_t)b * T.ldv + j0 + k) : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
@@ -308,10 +330,37 @@ __global__ void __launch_bounds__(256) batched_reduce_kernel(const __grid_consta
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + c;
-      if (i < T.ni && j < T.nj) T.out[(size_t)i * T.si + (size_t)j * T.sj] = acc[a][c];
+    for (int c = 0; c < 2; ++c) pout[(2 * ty + a) * 32 + 2 * tx + c] = acc[a][c];
+}
+
+// grid = tiles; sums the kReduceSplits partial tiles in fixed order and scatters to the gradient tensors.
+__global__ void __launch_bounds__(256) batched_reduce_finish_kernel(const __grid_constant__ ReduceTaskTable tab, const float* __restrict__ partial) {
+  int ti = 0;
+  while (ti + 1 < tab.n && tab.t[ti + 1].tile_begin <= (int)blockIdx.x) ++ti;
+  const ReduceTask& T = tab.t[ti];
+  const int tile = blockIdx.x - T.tile_begin;
+  const float* p = partial + (size_t)blockIdx.x * kReduceSplits * 1024;
+  if (T.V == nullptr) {
+    const int tx = threadIdx.x;
+    const int j = tile * 32 + tx;
+    if (tx < 32 && j < T.ni) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < kReduceSplits; ++k) t += p[k * 1024 + tx];
+      T.out[(size_t)j * T.si] = t;
     }
+    return;
+  }
+  const int i0 = (tile / T.tiles_j) * 32, j0 = (tile % T.tiles_j) * 32;
+  for (int e = threadIdx.x; e < 1024; e += 256) {
+    const int i = i0 + (e >> 5), j = j0 + (e & 31);
+    if (i < T.ni && j < T.nj) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < kReduceSplits; ++k) t += p[k * 1024 + e];
+      T.out[(size_t)i * T.si + (size_t)j * T.sj] = t;
+    }
+  }
 }
 
 __global__ void fill_zero_kernel(float* __restrict__ p, size_t n) {
