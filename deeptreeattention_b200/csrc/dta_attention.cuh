@@ -4,6 +4,7 @@
 // spectral_attention.forward :149-168, spatial_attention.forward :105-124, Classifier :63-66.
 #pragma once
 #include "dta_common.cuh"
+#include "dta_tc.cuh"
 
 namespace dta {
 
@@ -41,10 +42,10 @@ template <int C, int SPRE, bool POOL>
 __device__ __forceinline__ void build_r(const float* __restrict__ zsrc, const float* __restrict__ scale,
                                         const float* __restrict__ shift, float* s_z, float* s_r,
                                         unsigned char* s_arg) {
+  // s_z already holds the crop's conv output (bulk-copied by the caller, see attn_stage_in)
   using Cfg = AttnCfg<C, SPRE, POOL>;
   const int tid = threadIdx.x;
-  for (int i = tid; i < C * Cfg::HWPRE; i += kAttnThreads) s_z[i] = __ldg(zsrc + i);
-  __syncthreads();
+  (void)zsrc;
   if (POOL) {
     for (int i = tid; i < C * Cfg::HW; i += kAttnThreads) {
       const int c = i / Cfg::HW, p = i - c * Cfg::HW;
@@ -67,6 +68,22 @@ __device__ __forceinline__ void build_r(const float* __restrict__ zsrc, const fl
     }
   }
   __syncthreads();
+}
+
+// Stage contiguous per-crop blocks global -> shared with the bulk-copy engine (one instruction per block instead of a
+// load/store loop per thread; the kernels were stalled on exactly those loops).  Blocks are multiples of 16 bytes and
+// 16-byte aligned on both sides by construction of the saved / workspace layouts.  Thread 0 issues, everybody waits.
+__device__ __forceinline__ void attn_stage_in(uint64_t* bar, float* dst0, const float* src0, int n0, float* dst1, const float* src1,
+                                              int n1) {
+  if (threadIdx.x == 0) {
+    tc::mbar_init(bar, 1);
+    tc::mbar_fence_init();
+    tc::mbar_arrive_expect_tx(bar, (uint32_t)(n0 + (src1 ? n1 : 0)) * 4u);
+    tc::bulk_g2s(dst0, src0, (uint32_t)n0 * 4u, bar);
+    if (src1) tc::bulk_g2s(dst1, src1, (uint32_t)n1 * 4u, bar);
+  }
+  __syncthreads();            // barrier initialised before anyone polls it
+  tc::mbar_wait(bar, 0);
 }
 
 // k x k "same" stencil on an S x S plane held in shared memory (zero padding).
@@ -105,7 +122,9 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
   const int b = blockIdx.x, g = blockIdx.y, G = gridDim.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int btype = prm.btype[g];
+  __shared__ uint64_t stage_bar;
 
+  attn_stage_in(&stage_bar, s_z, z + ((size_t)b * G + g) * C * Cfg::HWPRE, C * Cfg::HWPRE, nullptr, nullptr, 0);
   build_r<C, SPRE, POOL>(z + ((size_t)b * G + g) * C * Cfg::HWPRE, scale + g * C, shift + g * C, s_z, s_r, nullptr);
 
   float* att_row = att + ((size_t)b * G + g) * Cfg::ATT_LD;
@@ -244,7 +263,11 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
   const float* sc = scale + g * C;
   const float* sh = shift + g * C;
   (void)feat_unused;
+  __shared__ uint64_t stage_bar;
 
+  // conv output of this crop and the upstream gradient of its gated feature map, one bulk copy each
+  const float* dsrc = dout ? dout + ((size_t)b * G + g) * C * HW : nullptr;
+  attn_stage_in(&stage_bar, s_z, z + ((size_t)b * G + g) * C * HWPRE, C * HWPRE, s_D, dsrc, C * HW);
   build_r<C, SPRE, POOL>(z + ((size_t)b * G + g) * C * HWPRE, sc, sh, s_z, s_r, POOL ? s_arg : nullptr);
 
   const float* att_row = att + ((size_t)b * G + g) * Cfg::ATT_LD;
@@ -265,9 +288,9 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
     }
     s_dfeat[f] = a;
   }
-  // upstream gradient of the gated feature map from the next conv's dgrad
-  const float* dsrc = dout ? dout + ((size_t)b * G + g) * C * HW : nullptr;
-  for (int i = tid; i < C * HW; i += kAttnThreads) s_D[i] = dsrc ? __ldg(dsrc + i) : 0.f;
+  // upstream gradient of the gated feature map from the next conv's dgrad: already staged; zero when absent
+  if (dsrc == nullptr)
+    for (int i = tid; i < C * HW; i += kAttnThreads) s_D[i] = 0.f;
   __syncthreads();
 
   float* prow_row = prow + ((size_t)b * G + g) * Row::LD;
