@@ -77,17 +77,17 @@ struct Carver {
 
 // Tensor-core path geometry.  Two position streams: side 11 (conv1, conv2 and their gradients) and
 // side 5 (conv3).  Buffers are padded so that every kernel's tile size divides the stream length.
-using WgradCfg1 = TcWgrad<48, 128, true>;    // conv1: merged 64 output channels (hi/lo stacked), 48-channel slices of the crops
+using WgradCfg1 = TcWgrad<128, 128, true, 3, 2>;  // conv1: merged 64 output channels (hi/lo stacked), 128-channel slices, 3 tap groups
 using WgradCfg2 = TcWgrad<32, 128, true>;    // conv2: 64 output channels per branch, 32 input channels
 using WgradCfg3 = TcWgrad<32, 64, false>;    // conv3: 128 output channels per branch, 2 slices of 32 input channels
 constexpr int kTcSmCount = 148;              // split-K factors are sized for the B200's 148 SMs (dta_query_sizes has no device)
 
 struct TcSplit { int nkstage, nslices, nsplit, per; };
-TcSplit tc_split(size_t rows, int krows, int cin_g, int nci, int G) {
+TcSplit tc_split(size_t rows, int krows, int cin_g, int nci, int G, int ntg = 1) {
   TcSplit t{};
   t.nkstage = (int)((rows - 2 * kTcGuard) / krows);
   t.nslices = (cin_g + nci - 1) / nci;
-  int want = kTcSmCount / (t.nslices * G);
+  int want = kTcSmCount / (t.nslices * G * ntg);
   if (want < 1) want = 1;
   if (want > t.nkstage) want = t.nkstage;
   t.per = (t.nkstage + want - 1) / want;
@@ -105,8 +105,8 @@ TcGeom tc_geom(int B, int bands, int nb) {
   g.rows11 = tc_rows(B, Stream<11>::PC, 1024);
   g.rows5 = tc_rows(B, Stream<5>::PC, 512);
   g.nstage1 = (bands + 15) / 16;
-  g.nchunk1 = (2 * g.nstage1 + 5) / 6 * 6;
-  g.w1 = tc_split(g.rows11, WgradCfg1::KROWS, g.nchunk1 * 8, WgradCfg1::NCI, 1);
+  g.nchunk1 = (2 * g.nstage1 + WgradCfg1::BCH - 1) / WgradCfg1::BCH * WgradCfg1::BCH;   // whole weight-gradient slices
+  g.w1 = tc_split(g.rows11, WgradCfg1::KROWS, g.nchunk1 * 8, WgradCfg1::NCI, 1, WgradCfg1::NTG);
   g.w2 = tc_split(g.rows11, WgradCfg2::KROWS, 32, WgradCfg2::NCI, nb);
   g.w3 = tc_split(g.rows5, WgradCfg3::KROWS, 64, WgradCfg3::NCI, nb);
   return g;
@@ -376,7 +376,7 @@ cudaError_t run_tc_wgrad(cudaStream_t st, const __nv_bfloat16* dzp, int dz_chunk
   auto kern = tc_conv_wgrad_kernel<S, Cfg>;
   cudaError_t e = allow_smem(kern, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  kern<<<dim3(sp.nslices, sp.nsplit, G), kTcThreads, Cfg::SMEM_BYTES, st>>>(dzp, dz_chunks, xp, x_chunks, rows, cin_g, cout_g, sp.nkstage,
+  kern<<<dim3(sp.nslices * Cfg::NTG, sp.nsplit, G), kTcThreads, Cfg::SMEM_BYTES, st>>>(dzp, dz_chunks, xp, x_chunks, rows, cin_g, cout_g, sp.nkstage,
                                                                           sp.per, part);
   return cudaGetLastError();
 }

@@ -429,11 +429,16 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
 //   9 taps x NCI columns of tensor memory.  Split-K over the stream: part[split][g][co][ci][tap], summed in
 //   fixed order by wgrad_reduce_kernel.
 // =======================================================================================
-template <int NCI_, int KROWS_, bool STACK_>
+//   NTG tap groups: the 9 taps are split over NTG CTAs (blockIdx.x = slice*NTG + group) that stream the same operands
+//   (the second reader hits L2); fewer taps per CTA leave tensor-memory room for wider N, and the per-MMA cost is
+//   32 + N/4 cycles of shared-memory operand reads against an N/2 issue floor (tools/tc_rate.cu), so wider N is faster.
+template <int NCI_, int KROWS_, bool STACK_, int NTG_ = 1, int NSTAGE_ = 3>
 struct TcWgrad {
   static constexpr int NCI = NCI_;                         // input channels per CTA slice
   static constexpr int KROWS = KROWS_;                     // stream positions per stage
   static constexpr bool STACK = STACK_;
+  static constexpr int NTG = NTG_;
+  static constexpr int MAXT = (9 + NTG - 1) / NTG;         // taps per CTA (first groups take the larger share)
   static constexpr int COUT = STACK ? 64 : 128;            // output channels per group
   static constexpr int AROWS = KROWS + 2 * kTcGuard;       // dz rows staged per chunk
   static constexpr int ACH = STACK ? 16 : 32;              // A chunks: [hi | lo]
@@ -441,10 +446,11 @@ struct TcWgrad {
   static constexpr int BCH = NCI / 8;
   static constexpr int B_BYTES = 2 * BCH * KROWS * 16;     // [half][BCH][KROWS][16 B]
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int NSTAGE = 3;
-  static constexpr int RED_BYTES = STACK ? 64 * NCI * 4 : 0;   // lo-half partials for the epilogue
-  static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + RED_BYTES + 1024;
-  static_assert(9 * NCI <= 512 && NCI % 16 == 0, "9 taps x NCI fp32 columns must fit tensor memory");
+  static constexpr int NSTAGE = NSTAGE_;
+  static constexpr int RED_BYTES = STACK ? 64 * NCI * 4 : 0;   // lo-half partials for the epilogue; aliases stage 0 (idle by then)
+  static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 1024;
+  static_assert(RED_BYTES <= STAGE_BYTES, "epilogue scratch must fit one stage");
+  static_assert(MAXT * NCI <= 512 && NCI % 16 == 0, "taps x NCI fp32 columns must fit tensor memory");
   static_assert(SMEM_BYTES <= 227 * 1024, "stage too large");
 };
 
@@ -456,14 +462,17 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows
   using St = Stream<S>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  float* s_red = reinterpret_cast<float*>(smem + (size_t)Cfg::NSTAGE * Cfg::STAGE_BYTES);
+  float* s_red = reinterpret_cast<float*>(smem);   // stage 0, reused once every MMA has completed (after tmem_full)
   __shared__ uint64_t full_bar[Cfg::NSTAGE], empty_bar[Cfg::NSTAGE], tmem_full;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int lane = tid & 31;
-  const int slice = blockIdx.x, split = blockIdx.y, g = blockIdx.z, G = gridDim.z;
+  const int slice = blockIdx.x / Cfg::NTG, tgroup = blockIdx.x % Cfg::NTG;
+  const int split = blockIdx.y, g = blockIdx.z, G = gridDim.z;
+  const int tap0 = tgroup * Cfg::MAXT;                          // this CTA's taps [tap0, tap0 + ntap)
+  const int ntap = min(Cfg::MAXT, 9 - tap0);
   const int ks_begin = split * stages_per_split;
   const int ks_end = min(nkstage_total, ks_begin + stages_per_split);
   const int nks = max(0, ks_end - ks_begin);
@@ -523,10 +532,11 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows
 #pragma unroll
       for (int kk = 0; kk < Cfg::KROWS / 16; ++kk) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
+        for (int tl = 0; tl < Cfg::MAXT; ++tl) {
+          const int t = tap0 + tl;
           const int arow = kTcGuard + kk * 16 - ((t / 3 - 1) * St::PT + (t % 3 - 1));   // dz row for input row kk*16
-          if (leader) {
-            const uint32_t dcol = tmem + t * Cfg::NCI;
+          if (leader && tl < ntap) {
+            const uint32_t dcol = tmem + tl * Cfg::NCI;
             tc::mma_bf16(dcol, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + kk * 16, b_hi32), idesc, (i | kk) ? 1u : 0u);
             tc::mma_bf16(dcol, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + B_LO_PLANE + kk * 16, b_hi32), idesc, 1u);
             if (!Cfg::STACK)
@@ -547,11 +557,12 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows
       tc::mbar_wait(&tmem_full, 0);
       tc::fence_after_sync();
     }
-    for (int t = 0; t < 9; ++t) {
+    for (int tl = 0; tl < ntap; ++tl) {
+      const int t = tap0 + tl;
       float v[Cfg::NCI];
       if (nks > 0) {
 #pragma unroll
-        for (int c0 = 0; c0 < Cfg::NCI; c0 += 16) tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + t * Cfg::NCI + c0, v + c0);
+        for (int c0 = 0; c0 < Cfg::NCI; c0 += 16) tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + tl * Cfg::NCI + c0, v + c0);
         tc::tmem_ld_wait();
       } else {
 #pragma unroll
