@@ -11,6 +11,7 @@
 #include "dta_conv_tc.cuh"
 #include "dta_loss.cuh"
 #include "dta_misc.cuh"
+#include "dta_preprocess.cuh"
 
 using namespace dta;
 
@@ -735,6 +736,20 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("forward: ") + cudaGetErrorString(e));
+  return DTA_OK;
+}
+
+int dta_preprocess_crops(dta_ctx* ctx, const int16_t* raw, int batch, int bands_in, int clip, float* out, void* cuda_stream) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  if (!raw || !out) return fail(ctx, DTA_ERR_INVALID_ARG, "raw and out are required");
+  if (batch <= 0 || bands_in <= 0 || clip < 0 || bands_in - 2 * clip <= 0) return fail(ctx, DTA_ERR_INVALID_ARG, "batch and bands_in - 2*clip must be positive");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
+  cudaGetLastError();
+  ctx->launches = 0;
+  StageScope sc(ctx, "data.preprocess_crops", st);
+  preprocess_crops_kernel<<<batch, 128 * kPrepSlices, 0, st>>>(reinterpret_cast<const short*>(raw), bands_in, kHW, clip, out);
+  DTA_CHECK_LAUNCH(ctx, "preprocess_crops");
   return DTA_OK;
 }
 

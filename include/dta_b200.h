@@ -184,6 +184,17 @@ int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, c
                             const int64_t* labels, const float* class_weight, float* loss,
                             float* const dscores[], void* workspace, void* cuda_stream);
 
+/*
+ * Raw crown crops -> network input, on the device.  Replaces utils.preprocess_image (src/utils.py:36-57) for
+ * crops that are already 11 x 11: drop `clip` bands at each end (the reference drops 10 when there are more than
+ * 3 bands), cast int16 -> float32, scale every pixel's spectrum to [0, 1] with the float32 arithmetic of
+ * sklearn.preprocessing.minmax_scale(axis=1) (bit-identical; constant spectra map to 0).
+ *   raw : (batch, bands_in, 11, 11) int16        out : (batch, bands_in - 2*clip, 11, 11) float32
+ * Lets the crops cross PCIe as int16 (half the bytes of the float32 tensors the reference's loader ships).
+ */
+int dta_preprocess_crops(dta_ctx* ctx, const int16_t* raw, int batch, int bands_in, int clip, float* out,
+                         void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,3 +100,21 @@ def test_same_seed_same_init_as_torch_layers():
         assert torch.equal(a[k], b[k])
     bound = 1.0 / (5 * 9) ** 0.5
     assert float(a["conv1.conv_layer.weight"].abs().max()) <= bound
+
+
+def test_year_and_metadata_modules_mirror_the_reference_surface():
+    """src/models/year.py:9-33 and src/models/metadata.py:9-44: constructors, parameter trees, CPU inputs refused."""
+    from deeptreeattention_b200 import metadata as M, year
+    e = year.learned_ensemble(years=3, classes=4, config={"bands": 5, "pretrain_state_dict": None})
+    assert len(e.year_models) == 3 and e.years == 3
+    assert sorted(k for k in e.state_dict() if k.startswith("year_models.0.classifier3")) == [
+        "year_models.0.classifier3.fc1.bias", "year_models.0.classifier3.fc1.weight"]
+    with pytest.raises(RuntimeError):
+        e([torch.randn(1, 5, 11, 11) for _ in range(3)])
+    f = M.metadata_sensor_fusion(bands=3, sites=2, classes=10)
+    keys = list(f.state_dict().keys())
+    assert keys[0] == "metadata_model.embedding.weight" and "sensor_model.alpha" in keys and keys[-1] == "fc1.bias"
+    assert f.fc1.weight.shape == (10, 20)
+    assert M.metadata(sites=1, classes=10)(torch.zeros(20).int()).shape == (20, 10)     # tests/test_metadata.py:11-15 (pure torch MLP)
+    with pytest.raises(RuntimeError):
+        f(torch.randn(2, 3, 11, 11), torch.zeros(2).int())

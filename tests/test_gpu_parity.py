@@ -220,3 +220,44 @@ def test_graphed_step_equals_eager_step():
     for (k, pe), (_, pg) in zip(me.named_parameters(), mg.named_parameters()):
         assert pg.grad is not None, k
         assert torch.equal(pe.grad, pg.grad), k
+
+
+def test_year_ensemble_matches_oracle_and_skips_zero_years():
+    """learned_ensemble (src/models/year.py:9-33; shapes of tests/test_year.py): mean of the last heads of the
+    non-zero years, each year network checked against the oracle."""
+    from deeptreeattention_b200 import year
+    bands, classes, B = 349, 6, 3
+    torch.manual_seed(0)
+    m = year.learned_ensemble(years=4, classes=classes, config={"bands": bands, "pretrain_state_dict": None}).cuda().eval()
+    images = [orc.make_inputs(B, bands, classes, 40 + i, "normal")[0] for i in range(3)] + [torch.zeros(B, bands, 11, 11)]
+    with torch.no_grad():
+        out = m([x.cuda() for x in images]).cpu()
+    assert out.shape == (B, classes)
+    ref = []
+    for i in range(3):
+        table = {k: v.detach().cpu() for k, v in m.year_models[i].state_dict().items()}
+        ref.append(orc.forward("spectral", table, images[i], training=False)[0][-1])
+    ref = torch.stack(ref, 1).mean(1)
+    np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=0, atol=SCORE_TOL)
+
+
+def test_metadata_sensor_fusion_matches_torch_reference():
+    """metadata_sensor_fusion (src/models/metadata.py:26-44, shapes of tests/test_metadata.py) in eval mode: the
+    Hang2020 part against the oracle, the site MLP / fusion layer with the same torch layers on the CPU."""
+    from deeptreeattention_b200 import metadata as M
+    bands, sites, classes, B = 30, 5, 10, 20
+    torch.manual_seed(1)
+    m = M.metadata_sensor_fusion(bands=bands, sites=sites, classes=classes).eval()
+    x, _ = orc.make_inputs(B, bands, classes, 9, "normal")
+    site = torch.randint(0, sites, (B,))
+    table = {k: v.detach().clone() for k, v in m.sensor_model.state_dict().items()}
+    joint, _ = orc.forward("hang2020", table, x, training=False)
+    with torch.no_grad():
+        ref = torch.relu(m.fc1(torch.cat([m.metadata_model(site), joint], dim=1)))
+        got = m.cuda()(x.cuda(), site.cuda()).cpu()
+    assert got.shape == (B, classes)
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=0, atol=SCORE_TOL)
+    m.train()
+    out = m(x.cuda(), site.cuda())
+    out.sum().backward()
+    assert m.sensor_model.alpha.grad is not None and m.fc1.weight.grad is not None
