@@ -12,8 +12,8 @@ import torch
 from . import _capi
 
 
-def preprocess_crops(raw: torch.Tensor, clip: int | None = None) -> torch.Tensor:
-    """raw: int16 CUDA tensor (B, bands_in, 11, 11) -> float32 (B, bands_in - 2*clip, 11, 11)."""
+def preprocess_crops(raw: torch.Tensor, clip: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """raw: int16 CUDA tensor (B, bands_in, 11, 11) -> float32 (B, bands_in - 2*clip, 11, 11) (written into ``out`` if given)."""
     if not raw.is_cuda:
         raise RuntimeError("deeptreeattention_b200 has no CPU path: move the raw crops to a CUDA (sm_100) device")
     if raw.dtype != torch.int16:
@@ -28,8 +28,12 @@ def preprocess_crops(raw: torch.Tensor, clip: int | None = None) -> torch.Tensor
     raw = raw.contiguous()
     dev = raw.device
     handle = _capi.context(dev.index if dev.index is not None else torch.cuda.current_device())
+    shape = (B, C - 2 * clip, 11, 11)
+    if out is not None and (out.dtype != torch.float32 or tuple(out.shape) != shape or not out.is_contiguous() or out.device != dev):
+        raise ValueError(f"out must be a contiguous float32 CUDA tensor of shape {shape}")
     with torch.cuda.device(dev):
-        out = torch.empty((B, C - 2 * clip, 11, 11), dtype=torch.float32, device=dev)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=dev)
         rc = _capi.lib().dta_preprocess_crops(handle, raw.data_ptr(), B, C, clip, out.data_ptr(),
                                               torch.cuda.current_stream(dev).cuda_stream)
     _capi.check(handle, rc, "dta_preprocess_crops")

@@ -42,6 +42,12 @@ class GraphedTrainStep:
                 after_backward()
             return loss
 
+        # gradients are produced on the capture / warm-up stream while the AccumulateGrad nodes were created on the
+        # default stream: intended here (everything is re-recorded into the graph), so silence the advisory
+        try:
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:      # older torch
+            pass
         side = torch.cuda.Stream(self.x.device)
         side.wait_stream(torch.cuda.current_stream(self.x.device))
         with torch.cuda.stream(side):
