@@ -30,9 +30,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line here
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION / WARN; stdout carries exactly one JSON line here
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    os.environ.pop("NCCL_DEBUG")
 
 import torch  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
@@ -449,7 +449,7 @@ def run_b200(args):
         "config": {"workload": f"Hang2020(bands={bands}, classes={classes}) fwd+CE({args.regime})+bwd"
                                + ("+grad all-reduce" if world > 1 else "") + f", {B} crops per GPU per step",
                    "regime": args.regime, "launch": "cuda-graph replay" if args.graph else "eager", "batch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"dp{world}", "l2": f"crops per step = {B * bands * 484 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
+                   "parallelism": f"dp{world}", "gradient_exchange": sync.last_path if world > 1 else None, "l2": f"crops per step = {B * bands * 484 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
                    if B * bands * 484 > 126e6 else "flush: none (inputs smaller than L2)"},
         "roofline": roof, "cpu_baseline": cpu, "clocks": clock_rec,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_dev.numel() * 4, "d2h_bytes_per_step": 4,

@@ -78,6 +78,9 @@ class _NetSpec:
         # .grad is a view of, and alpha's fp64 gradient (distributed.GradSync reduces these)
         self.flat_grad = None
         self.alpha_grad = None
+        # optional persistent (flat float32, 0-dim float64) gradient buffers supplied by distributed.GradSync: symmetric
+        # memory that the peer all-reduce kernel works on in place
+        self.grad_buffers = None
         self._table_key = None
         self._table = None
 
@@ -146,8 +149,14 @@ class _FusedNetFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             # every float gradient lives in ONE flat buffer (a single all-reduce covers it)
             numels = [p.numel() if p.dtype == torch.float32 else 0 for p in params]
-            flat = torch.zeros(sum(numels), dtype=torch.float32, device=dev)
-            galpha = torch.zeros((), dtype=torch.float64, device=dev)
+            bufs = spec.grad_buffers
+            if bufs is not None and bufs[0].numel() == sum(numels) and bufs[0].device == dev:
+                flat, galpha = bufs
+                flat.zero_()
+                galpha.zero_()
+            else:
+                flat = torch.zeros(sum(numels), dtype=torch.float32, device=dev)
+                galpha = torch.zeros((), dtype=torch.float64, device=dev)
             grads, off = [], 0
             for p, n in zip(params, numels):
                 if p.dtype == torch.float32:
@@ -207,6 +216,7 @@ class _FusedNet(Module):
             cache = (names, params, buffers, _NetSpec(self._net_kind, self._bands, self._classes), next(self.buffers()))
             self.__dict__["_fused_cache"] = cache
         names, params, buffers, spec = cache[:4]
+        spec.grad_buffers = self.__dict__.get("_grad_buffers")
         if params[0].device != x.device:
             raise RuntimeError(f"parameter on {params[0].device} but crops on {x.device}")
         return _FusedNetFunction.apply(x, spec, self.training, names, buffers, *params)

@@ -55,7 +55,7 @@ class StageTime(C.Structure):
 
 EXPORTS = ["dta_abi_version", "dta_create", "dta_destroy", "dta_last_error", "dta_set_option", "dta_get_option",
            "dta_profile_read", "dta_query_sizes", "dta_forward", "dta_backward", "dta_loss_workspace_bytes",
-           "dta_cross_entropy_heads", "dta_preprocess_crops"]
+           "dta_cross_entropy_heads", "dta_preprocess_crops", "dta_grad_allreduce_sizes", "dta_grad_allreduce"]
 
 
 def sources():
@@ -137,6 +137,12 @@ def lib():
         L.dta_cross_entropy_heads.restype = C.c_int
         L.dta_preprocess_crops.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.dta_preprocess_crops.restype = C.c_int
+        L.dta_grad_allreduce_sizes.argtypes = [C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                               C.POINTER(C.c_size_t)]
+        L.dta_grad_allreduce_sizes.restype = C.c_int
+        L.dta_grad_allreduce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p * 16), C.c_void_p, C.c_size_t, C.c_size_t,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+        L.dta_grad_allreduce.restype = C.c_int
         _lib = L
         return L
 

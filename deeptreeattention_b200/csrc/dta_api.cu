@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "dta_attention.cuh"
+#include "dta_collective.cuh"
 #include "dta_common.cuh"
 #include "dta_conv_simt.cuh"
 #include "dta_conv_tc.cuh"
@@ -750,6 +751,39 @@ int dta_preprocess_crops(dta_ctx* ctx, const int16_t* raw, int batch, int bands_
   StageScope sc(ctx, "data.preprocess_crops", st);
   preprocess_crops_kernel<<<batch, 128 * kPrepSlices, 0, st>>>(reinterpret_cast<const short*>(raw), bands_in, kHW, clip, out);
   DTA_CHECK_LAUNCH(ctx, "preprocess_crops");
+  return DTA_OK;
+}
+
+int dta_grad_allreduce_sizes(size_t n_float4, size_t n_double, int world, size_t* buffer_bytes, size_t* flags_offset, size_t* scratch_bytes) {
+  if (world < 1 || world > kMaxPeers || !buffer_bytes || !scratch_bytes) return DTA_ERR_INVALID_ARG;
+  *buffer_bytes = ar_buffer_bytes(n_float4, n_double, world);
+  if (flags_offset) *flags_offset = ar_flags_offset(n_float4, n_double);
+  *scratch_bytes = n_float4 * 16 + n_double * 8 + 16;
+  return DTA_OK;
+}
+
+int dta_grad_allreduce(dta_ctx* ctx, int rank, int world, void* const peer_buffers[], const void* multicast_buffer, size_t n_float4,
+                       size_t n_double, void* scratch, void* sync_words, void* cuda_stream) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(ctx, DTA_ERR_INVALID_ARG, "need 0 <= rank < world <= 16");
+  if (!peer_buffers || !scratch || !sync_words) return fail(ctx, DTA_ERR_INVALID_ARG, "peer_buffers, scratch and sync_words are required");
+  PeerPtrs pp{};
+  for (int r = 0; r < world; ++r) {
+    if (!peer_buffers[r]) return fail(ctx, DTA_ERR_INVALID_ARG, "peer_buffers[r] is NULL");
+    pp.buf[r] = static_cast<float*>(peer_buffers[r]);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
+  cudaGetLastError();
+  ctx->launches = 0;
+  StageScope sc(ctx, "dist.grad_allreduce", st);
+  // every CTA spins on flags, so the grid must be co-resident: far below one CTA per SM
+  int grid = (int)((n_float4 + kArThreads - 1) / kArThreads);
+  if (grid > 64) grid = 64;
+  if (grid < 1) grid = 1;
+  grad_allreduce_kernel<<<grid, kArThreads, 0, st>>>(pp, static_cast<const float*>(multicast_buffer), rank, world, n_float4, n_double,
+                                                     static_cast<float*>(scratch), static_cast<uint32_t*>(sync_words));
+  DTA_CHECK_LAUNCH(ctx, "grad_allreduce");
   return DTA_OK;
 }
 

@@ -47,15 +47,22 @@ class GradSync:
     """Averages the gradients of ``module`` over the process group after ``backward()``.
 
     Fast path: the fused backward left all float32 gradients as views of one flat buffer ->
-    one all-reduce on it (alpha's float64 gradient rides in the same coalesced launch).
+    one all-reduce on it (plus 8 bytes for alpha's float64 gradient).
     Generic path (any module, e.g. the CPU oracle in the gloo tests, or gradients that were
     accumulated/replaced): flatten per dtype, all-reduce, scatter back.
     """
 
-    def __init__(self, module: torch.nn.Module, group=None):
+    def __init__(self, module: torch.nn.Module, group=None, peer: bool = True):
         self.module, self.group = module, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.last_path = None
+        self.peer = None
+        self.peer_error = None
+        if peer and self.world > 1 and hasattr(module, "fused_spec") and next(module.parameters()).is_cuda:
+            try:
+                self.peer = _PeerBuffers(module, group)
+            except Exception as e:      # no symmetric memory on this system / torch build: NCCL path
+                self.peer_error = f"{type(e).__name__}: {e}"
 
     def _flat_views_intact(self, spec) -> bool:
         flat = getattr(spec, "flat_grad", None) if spec is not None else None
@@ -75,14 +82,18 @@ class GradSync:
             self.last_path = "single"
             return
         spec = self.module.fused_spec() if hasattr(self.module, "fused_spec") else None
+        if self.peer is not None and spec is not None and spec.flat_grad is self.peer.flat and self._flat_views_intact(spec):
+            # ONE kernel over NVLink peer memory: sum over ranks (in the switch when NVLS is available), mean, in place
+            self.peer.allreduce()
+            self.last_path = "peer-multimem" if self.peer.multicast_ptr else "peer-p2p"
+            return
         if self._flat_views_intact(spec):
             flat, galpha = spec.flat_grad, spec.alpha_grad
             tensors = [flat] + ([galpha] if galpha is not None else [])
             if flat.is_cuda:
-                # NCCL averages in the collective itself; both tensors go out in one group launch
-                with dist._coalescing_manager(group=self.group, device=flat.device, async_ops=False):
-                    for t in tensors:
-                        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+                # NCCL averages in the collective itself (alpha's float64 gradient cannot be coalesced with float32)
+                for t in tensors:
+                    dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
             else:
                 for t in tensors:
                     dist.all_reduce(t, group=self.group)
@@ -109,3 +120,53 @@ def broadcast_buffers(module: torch.nn.Module, src: int = 0, group=None):
         return
     for b in module.buffers():
         dist.broadcast(b, src=src, group=group)
+
+
+class _PeerBuffers:
+    """Symmetric-memory gradient buffers of one module + the fused all-reduce call (dta_grad_allreduce)."""
+
+    def __init__(self, module: torch.nn.Module, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _capi
+        params = list(module.parameters())
+        dev = params[0].device
+        nfloat = sum(p.numel() for p in params if p.dtype == torch.float32)
+        ndouble = sum(p.numel() for p in params if p.dtype == torch.float64)
+        if any(p.dtype not in (torch.float32, torch.float64) for p in params) or ndouble > 1:
+            raise ValueError("peer gradient buffers support float32 parameters plus the float64 alpha")
+        self.n4 = (nfloat + 3) // 4
+        self.nd = ndouble
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        lib = _capi.lib()
+        buf_bytes, flags_off, scratch_bytes = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        if lib.dta_grad_allreduce_sizes(self.n4, self.nd, self.world, C.byref(buf_bytes), C.byref(flags_off), C.byref(scratch_bytes)) != 0:
+            raise ValueError(f"world size {self.world} not supported by the peer all-reduce")
+        with torch.cuda.device(dev):
+            self.buf = symm_mem.empty(buf_bytes.value, dtype=torch.uint8, device=dev)
+            self.buf.zero_()
+            self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            self.scratch = torch.empty(scratch_bytes.value, dtype=torch.uint8, device=dev)
+            self.sync_words = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.peer_ptrs = (C.c_void_p * 16)(*[int(p) for p in self.handle.buffer_ptrs] + [None] * (16 - self.world))
+        try:
+            self.multicast_ptr = int(self.handle.multicast_ptr) if self.handle.has_multicast_support(dev.type, dev.index) else 0
+        except Exception:
+            self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        self.flat = self.buf[:nfloat * 4].view(torch.float32)
+        self.alpha = self.buf[self.n4 * 16:self.n4 * 16 + 8].view(torch.float64).reshape(()) if ndouble else torch.zeros((), dtype=torch.float64, device=dev)
+        self.device, self._capi, self._C = dev, _capi, C
+        module.__dict__["_grad_buffers"] = (self.flat, self.alpha)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group)          # every rank's flag words are zero before anyone signals
+
+    def allreduce(self):
+        dev = self.device
+        handle = self._capi.context(dev.index)
+        rc = self._capi.lib().dta_grad_allreduce(handle, self.rank, self.world, self._C.byref(self.peer_ptrs), self.multicast_ptr or None,
+                                                 self.n4, self.nd, self.scratch.data_ptr(), self.sync_words.data_ptr(),
+                                                 torch.cuda.current_stream(dev).cuda_stream)
+        self._capi.check(handle, rc, "dta_grad_allreduce")

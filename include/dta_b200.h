@@ -195,6 +195,23 @@ int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, c
 int dta_preprocess_crops(dta_ctx* ctx, const int16_t* raw, int batch, int bands_in, int clip, float* out,
                          void* cuda_stream);
 
+/*
+ * Gradient exchange of data-parallel training as ONE kernel over NVLink / NVSwitch peer memory.  Replaces the
+ * gradient all-reduce (mean) that Lightning's DDP wrapper would issue through NCCL when the reference trains with
+ * gpus > 1 (train.py:89-98).
+ *   peer_buffers[r]  : rank r's gradient buffer as mapped in THIS process (symmetric memory; [rank] is local).
+ *                      Layout: n_float4 * 16 bytes of float32 gradients, n_double float64 values, then the flag words
+ *                      at flags_offset (dta_grad_allreduce_sizes); the flag words must be zero before the first call.
+ *   multicast_buffer : NVSwitch multicast mapping of the same buffers (multimem.ld_reduce sums in the switch), or NULL
+ *                      (plain loads from every peer, summed in rank order)
+ *   scratch          : scratch_bytes of local device memory; sync_words: 4 zero-initialised uint32 of local memory
+ * On return (stream order) the local buffer holds the MEAN over ranks; every rank must make the same call.
+ */
+int dta_grad_allreduce_sizes(size_t n_float4, size_t n_double, int world, size_t* buffer_bytes, size_t* flags_offset,
+                             size_t* scratch_bytes);
+int dta_grad_allreduce(dta_ctx* ctx, int rank, int world, void* const peer_buffers[], const void* multicast_buffer,
+                       size_t n_float4, size_t n_double, void* scratch, void* sync_words, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
