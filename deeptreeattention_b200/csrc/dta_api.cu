@@ -989,6 +989,11 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     StageScope sc(ctx, "bwd.wgrad_reduce", st);
     MutPtr2 dw{{grads->branch[0].conv[k].conv_w, nb > 1 ? grads->branch[1].conv[k].conv_w : nullptr}};
     const size_t per_branch = (size_t)kC[k] * cin * 9;
+    if (tcp) {
+      // tensor-core partials are [split][g][tap][ci][co]; conv1 is one group over both branches' output channels
+      const int G = k == 0 ? 1 : nb, cout_g = k == 0 ? nb * kC[0] : kC[k];
+      tc_wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W.wpart, nsplit, G, cout_g, cin, dw, per_branch);
+    } else
     wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W.wpart, nsplit, 1, per_branch * nb, dw, per_branch);
     DTA_CHECK_LAUNCH(ctx, "wgrad_reduce");
     return DTA_OK;

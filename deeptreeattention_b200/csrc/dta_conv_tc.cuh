@@ -580,10 +580,11 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows
         }
       }
       if (row < Cfg::COUT && row < cout_g) {
-        float* dst = part + ((((size_t)split * G + g) * cout_g + row) * cin_g + (size_t)slice * Cfg::NCI) * 9 + t;
+        // partial layout [split][g][tap][ci][co]: a warp's 32 rows (co) are contiguous -> coalesced stores
+        float* dst = part + ((((size_t)split * G + g) * 9 + t) * cin_g + (size_t)slice * Cfg::NCI) * cout_g + row;
 #pragma unroll
         for (int j = 0; j < Cfg::NCI; ++j)
-          if (slice * Cfg::NCI + j < cin_g) dst[(size_t)j * 9] = v[j];
+          if (slice * Cfg::NCI + j < cin_g) dst[(size_t)j * cout_g] = v[j];
       }
       if (Cfg::STACK) epi_bar_sync();
     }
@@ -591,6 +592,26 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+// dW[g][co][ci][tap] = sum_s part[s][g][tap][ci][co] (fixed order).  Reads are coalesced along co; the destination is the
+// reference's (cout, cin, 3, 3) tensor, or two of them when one group covers both branches (conv1).
+__global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int G, int cout_g, int cin_g, MutPtr2 dw,
+                                       size_t ptr_split /*elements per destination tensor*/) {
+  const size_t per_split = (size_t)G * 9 * cin_g * cout_g;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_split; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < nsplit; ++k) s += __ldg(part + (size_t)k * per_split + i);
+    size_t r = i;
+    const int co = (int)(r % cout_g); r /= cout_g;
+    const int ci = (int)(r % cin_g); r /= cin_g;
+    const int t = (int)(r % 9); r /= 9;
+    const int g = (int)r;
+    const size_t flat = (((size_t)g * cout_g + co) * cin_g + ci) * 9 + t;   // index in [G][cout][cin][9]
+    const size_t q = flat / ptr_split;
+    float* d = dw.p[q];
+    if (d != nullptr) d[flat - q * ptr_split] = s;
+  }
 }
 
 // Per-channel sum / sum of squares of z[b][c][hw] over groups of crops (BatchNorm batch statistics
