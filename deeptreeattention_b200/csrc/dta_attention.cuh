@@ -40,12 +40,12 @@ struct AttnCfg {
 // slot of every pooled cell, first-max rule of ATen max_pool2d).
 template <int C, int SPRE, bool POOL>
 __device__ __forceinline__ void build_r(const float* __restrict__ zsrc, const float* __restrict__ scale,
-                                        const float* __restrict__ shift, float* s_z, float* s_r,
-                                        unsigned char* s_arg) {
-  // s_z already holds the crop's conv output (bulk-copied by the caller, see attn_stage_in)
+                                        const float* __restrict__ shift, float* s_r, unsigned char* s_arg) {
+  // POOL: the 2x2 windows are read straight from global memory (each conv output element is needed once, so staging
+  // the pre-pool plane would only cost shared memory and occupancy).  !POOL: s_r already holds the crop's conv
+  // output, bulk-copied by the caller (attn_stage_in), and is rectified in place.
   using Cfg = AttnCfg<C, SPRE, POOL>;
   const int tid = threadIdx.x;
-  (void)zsrc;
   if (POOL) {
     for (int i = tid; i < C * Cfg::HW; i += kAttnThreads) {
       const int c = i / Cfg::HW, p = i - c * Cfg::HW;
@@ -55,7 +55,7 @@ __device__ __forceinline__ void build_r(const float* __restrict__ zsrc, const fl
       int arg = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float a = fmaxf(fmaf(s_z[c * Cfg::HWPRE + (2 * y + (k >> 1)) * SPRE + 2 * x + (k & 1)], sc, sh), 0.f);
+        const float a = fmaxf(fmaf(__ldg(zsrc + c * Cfg::HWPRE + (2 * y + (k >> 1)) * SPRE + 2 * x + (k & 1)), sc, sh), 0.f);
         if (a > best) { best = a; arg = k; }
       }
       s_r[i] = best;
@@ -64,7 +64,7 @@ __device__ __forceinline__ void build_r(const float* __restrict__ zsrc, const fl
   } else {
     for (int i = tid; i < C * Cfg::HW; i += kAttnThreads) {
       const int c = i / Cfg::HW;
-      s_r[i] = fmaxf(fmaf(s_z[i], __ldg(scale + c), __ldg(shift + c)), 0.f);
+      s_r[i] = fmaxf(fmaf(s_r[i], __ldg(scale + c), __ldg(shift + c)), 0.f);
     }
   }
   __syncthreads();
@@ -114,8 +114,7 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
   using Cfg = AttnCfg<C, SPRE, POOL>;
   constexpr int S = Cfg::S, HW = Cfg::HW;
   extern __shared__ __align__(16) float smem[];
-  float* s_z = smem;                       // C*HWPRE
-  float* s_r = POOL ? (s_z + C * Cfg::HWPRE) : s_z;   // in-place when there is no pooling
+  float* s_r = smem;                       // C*HW rectified (pooled) activations; !POOL: receives z first
   float* s_v = s_r + C * HW;               // 3*ROW vectors
   float* s_feat = s_v + 3 * Cfg::ROW;      // FEAT_LD
 
@@ -124,8 +123,9 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
   const int btype = prm.btype[g];
   __shared__ uint64_t stage_bar;
 
-  attn_stage_in(&stage_bar, s_z, z + ((size_t)b * G + g) * C * Cfg::HWPRE, C * Cfg::HWPRE, nullptr, nullptr, 0);
-  build_r<C, SPRE, POOL>(z + ((size_t)b * G + g) * C * Cfg::HWPRE, scale + g * C, shift + g * C, s_z, s_r, nullptr);
+  const float* zg = z + ((size_t)b * G + g) * C * Cfg::HWPRE;
+  if (!POOL) attn_stage_in(&stage_bar, s_r, zg, C * Cfg::HWPRE, nullptr, nullptr, 0);
+  build_r<C, SPRE, POOL>(zg, scale + g * C, shift + g * C, s_r, nullptr);
 
   float* att_row = att + ((size_t)b * G + g) * Cfg::ATT_LD;
   float* feat_row = feat + ((size_t)b * G + g) * Cfg::FEAT_LD;
@@ -219,7 +219,7 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
 template <int C, int SPRE, bool POOL>
 constexpr size_t attn_fwd_smem() {
   using Cfg = AttnCfg<C, SPRE, POOL>;
-  return sizeof(float) * ((POOL ? C * Cfg::HWPRE : 0) + C * Cfg::HW + 3 * Cfg::ROW + Cfg::FEAT_LD);
+  return sizeof(float) * (C * Cfg::HW + 3 * Cfg::ROW + Cfg::FEAT_LD);
 }
 
 // ------------------------------------------------------------------------------ backward
@@ -248,8 +248,7 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
   using Row = AttnBwdRow<C, SPRE, POOL>;
   constexpr int S = Cfg::S, HW = Cfg::HW, HWPRE = Cfg::HWPRE;
   extern __shared__ __align__(16) float smem[];
-  float* s_z = smem;                       // C*HWPRE raw conv output
-  float* s_r = s_z + C * HWPRE;            // C*HW
+  float* s_r = smem;                       // C*HW rectified (pooled) activations; !POOL: receives z first
   float* s_D = s_r + C * HW;               // C*HW  gradient wrt gated output, then wrt r
   float* s_v = s_D + C * HW;               // 3*ROW saved attention vectors
   float* s_w = s_v + 3 * Cfg::ROW;         // 4*ROW work vectors
@@ -267,8 +266,10 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
 
   // conv output of this crop and the upstream gradient of its gated feature map, one bulk copy each
   const float* dsrc = dout ? dout + ((size_t)b * G + g) * C * HW : nullptr;
-  attn_stage_in(&stage_bar, s_z, z + ((size_t)b * G + g) * C * HWPRE, C * HWPRE, s_D, dsrc, C * HW);
-  build_r<C, SPRE, POOL>(z + ((size_t)b * G + g) * C * HWPRE, sc, sh, s_z, s_r, POOL ? s_arg : nullptr);
+  const float* zg = z + ((size_t)b * G + g) * C * HWPRE;
+  if (!POOL) attn_stage_in(&stage_bar, s_r, zg, C * HWPRE, s_D, dsrc, C * HW);
+  else if (dsrc != nullptr) attn_stage_in(&stage_bar, s_D, dsrc, C * HW, nullptr, nullptr, 0);
+  build_r<C, SPRE, POOL>(zg, sc, sh, s_r, POOL ? s_arg : nullptr);
 
   const float* att_row = att + ((size_t)b * G + g) * Cfg::ATT_LD;
   for (int i = tid; i < 3 * Cfg::ROW; i += kAttnThreads) s_v[i] = __ldg(att_row + i);
@@ -450,7 +451,7 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
     const float mu = __ldg(mean + g * C + c), is = __ldg(istd + g * C + c);
     float s1 = 0.f, s2 = 0.f;
     for (int pp = lane; pp < HWPRE; pp += 32) {
-      const float zv = s_z[c * HWPRE + pp];
+      const float zv = __ldg(zg + c * HWPRE + pp);     // second read of z (L2-resident), instead of keeping it in smem
       const float a = fmaf(zv, scv, shv);
       float dv = 0.f;
       if (POOL) {
@@ -476,7 +477,7 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
 template <int C, int SPRE, bool POOL>
 size_t attn_bwd_smem(int classes) {
   using Cfg = AttnCfg<C, SPRE, POOL>;
-  const size_t floats = (size_t)C * Cfg::HWPRE + 2 * C * Cfg::HW + 7 * Cfg::ROW + Cfg::FEAT_LD + ((classes + 3) / 4) * 4;
+  const size_t floats = (size_t)2 * C * Cfg::HW + 7 * Cfg::ROW + Cfg::FEAT_LD + ((classes + 3) / 4) * 4;
   return floats * sizeof(float) + (size_t)C * Cfg::HW;
 }
 
