@@ -661,7 +661,8 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     auto kern = attn_fwd_kernel<32, 11, false>;
     const size_t sm = attn_fwd_smem<32, 11, false>();
     allow_smem(kern, sm);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], attn_params(params, L, d, 0, false), classes, L.att[0], L.feat[0], score_ptrs(0));
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], attn_params(params, L, d, 0, false), classes, L.att[0], L.feat[0], score_ptrs(0),
+                                              tcp ? L.a1p : nullptr, tg.rows11, nb * 4);
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<1>");
   }
   // 3. block 2
@@ -669,7 +670,12 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     ConvSrc src = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
     {
       StageScope sc(ctx, "fwd.conv2_pack", st);
-      DTA_TC_CHECK(run_tc_pack<11>(ctx, st, src, nb, B, nb * 4, tg.rows11, L.a1p), "tc_pack_stream(act1)");
+      if (vanilla) {
+        DTA_TC_CHECK(run_tc_pack<11>(ctx, st, src, nb, B, nb * 4, tg.rows11, L.a1p), "tc_pack_stream(act1)");
+      } else {   // block 1's attention kernel already wrote the crop rows of a1p
+        tc_zero_guards_kernel<<<32, 256, 0, st>>>(L.a1p, tg.rows11, nb * 4, (size_t)B * Stream<11>::PC);
+        DTA_CHECK_LAUNCH(ctx, "tc_zero_guards");
+      }
       tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, st>>>(conv_w(1), nb, 64, 32, 2, 1, W.wpf[1]);
       DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
     }
@@ -692,7 +698,8 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     auto kern = attn_fwd_kernel<64, 11, true>;
     const size_t sm = attn_fwd_smem<64, 11, true>();
     allow_smem(kern, sm);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], attn_params(params, L, d, 1, false), classes, L.att[1], L.feat[1], score_ptrs(1));
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], attn_params(params, L, d, 1, false), classes, L.att[1], L.feat[1], score_ptrs(1),
+                                              tcp ? L.a2p : nullptr, tg.rows5, nb * 8);
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<2>");
   }
   // 4. block 3
@@ -700,7 +707,12 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     ConvSrc src = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
     {
       StageScope sc(ctx, "fwd.conv3_pack", st);
-      DTA_TC_CHECK(run_tc_pack<5>(ctx, st, src, nb, B, nb * 8, tg.rows5, L.a2p), "tc_pack_stream(act2)");
+      if (vanilla) {
+        DTA_TC_CHECK(run_tc_pack<5>(ctx, st, src, nb, B, nb * 8, tg.rows5, L.a2p), "tc_pack_stream(act2)");
+      } else {
+        tc_zero_guards_kernel<<<32, 256, 0, st>>>(L.a2p, tg.rows5, nb * 8, (size_t)B * Stream<5>::PC);
+        DTA_CHECK_LAUNCH(ctx, "tc_zero_guards");
+      }
       tc_pack_w_fprop_kernel<128><<<ctx->sm_count, 256, 0, st>>>(conv_w(2), nb, 128, 64, 4, 1, W.wpf[2]);
       DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
     }
@@ -723,7 +735,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     auto kern = attn_fwd_kernel<128, 5, true>;
     const size_t sm = attn_fwd_smem<128, 5, true>();
     allow_smem(kern, sm);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], attn_params(params, L, d, 2, vanilla), classes, L.att[2], L.feat[2], score_ptrs(2));
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], attn_params(params, L, d, 2, vanilla), classes, L.att[2], L.feat[2], score_ptrs(2), nullptr, 0, 0);
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<3>");
   }
   // 5. alpha blend + copies of the last-head scores for dalpha

@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __restrict__ scale,
                 const float* __restrict__ shift, AttnParams prm, int classes,
                 float* __restrict__ att /*[B][G][ATT_LD]*/, float* __restrict__ feat /*[B][G][FEAT_LD]*/,
-                MutPtr2 scores /*per branch [B][classes]*/) {
+                MutPtr2 scores /*per branch [B][classes]*/,
+                __nv_bfloat16* __restrict__ packed /*split-bf16 position stream of the gated output (next conv's operand) or null*/,
+                size_t packed_rows, int packed_nchunk) {
   using Cfg = AttnCfg<C, SPRE, POOL>;
   constexpr int S = Cfg::S, HW = Cfg::HW;
   extern __shared__ __align__(16) float smem[];
@@ -203,6 +205,38 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
     F = C * HW;
   }
   __syncthreads();
+  if (packed != nullptr) {
+    // The gated feature map r * s is the next convolution's input: write it straight into that kernel's operand
+    // format (dta_conv_tc.cuh position stream: pad row above / pad column right of the plane, 8-channel chunks,
+    // hi and lo bf16 planes) -- same arithmetic as tc_pack_stream_kernel<SRC_ACT>, without re-reading z.
+    constexpr int PT = S + 1, PC = (S + 1) * PT;
+    const float* s_s = s_v + 2 * Cfg::ROW;
+    uint4* dst = reinterpret_cast<uint4*>(packed);
+    const size_t lo_off = packed_rows * packed_nchunk;
+    for (int u = tid; u < (C / 8) * PC; u += kAttnThreads) {
+      const int c8 = u / PC, r = u - c8 * PC;
+      const int yy = r / PT, xx = r - yy * PT;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      if (yy >= 1 && xx < S) {
+        const int p = (yy - 1) * S + xx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float a = s_r[(c8 * 8 + j) * HW + p];
+          v[j] = btype == BR_SPECTRAL ? a * s_s[c8 * 8 + j] : (btype == BR_SPATIAL ? a * s_s[p] : a);
+        }
+      }
+      uint4 hi, lo;
+      tc::split2(v[0], v[1], hi.x, lo.x);
+      tc::split2(v[2], v[3], hi.y, lo.y);
+      tc::split2(v[4], v[5], hi.z, lo.z);
+      tc::split2(v[6], v[7], hi.w, lo.w);
+      const size_t idx = (size_t)(g * (C / 8) + c8) * packed_rows + kTcGuard + (size_t)b * PC + r;
+      dst[idx] = hi;
+      dst[lo_off + idx] = lo;
+    }
+  }
   for (int f = tid; f < F; f += kAttnThreads) feat_row[f] = s_feat[f];
   const float* fw = prm.fc_w[g];
   if (fw != nullptr) {

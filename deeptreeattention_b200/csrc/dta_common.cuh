@@ -11,6 +11,7 @@ constexpr int kSide = DTA_IMAGE_SIZE;  // 11
 constexpr int kHW = kSide * kSide;     // 121
 constexpr float kBnEps = 1e-5f;        // nn.BatchNorm2d default (Hang2020.py:19)
 constexpr float kBnMomentum = 0.1f;
+constexpr int kTcGuard = 16;           // zero rows before the first / after the last crop of a packed position stream (dta_conv_tc.cuh)
 
 // Attention flavour of a branch.
 enum BranchType : int { BR_NONE = 0, BR_SPECTRAL = 1, BR_SPATIAL = 2 };

@@ -20,7 +20,6 @@
 
 namespace dta {
 
-constexpr int kTcGuard = 16;       // zero rows before the first / after the last crop (>= PT + 1)
 constexpr int kTcThreads = 192;    // warp 0: bulk-copy producer, warp 1: MMA issuer, warps 2-5: epilogue
 
 __device__ __forceinline__ uint32_t elect_one_sync() {
@@ -136,6 +135,19 @@ tc_pack_stream_kernel(ConvSrc src, int G, int B, int nchunk, size_t rows, __nv_b
     tc::split2(v[6], v[7], hi.w, lo.w);
     reinterpret_cast<uint4*>(dst)[i] = hi;
     reinterpret_cast<uint4*>(dst)[total + i] = lo;
+  }
+}
+
+// Zero the guard rows [0, GUARD) and the tail rows [GUARD + valid, rows) of every (half, chunk) plane of a packed stream
+// whose crop rows are written by another kernel (the attention kernels pack their own output).
+__global__ void tc_zero_guards_kernel(__nv_bfloat16* __restrict__ dst, size_t rows, int nchunk, size_t valid) {
+  const size_t tail0 = kTcGuard + valid;
+  const size_t per_plane = kTcGuard + (rows - tail0);
+  const size_t total = per_plane * nchunk * 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t plane = i / per_plane, r = i - plane * per_plane;
+    const size_t row = r < (size_t)kTcGuard ? r : tail0 + (r - kTcGuard);
+    reinterpret_cast<uint4*>(dst)[plane * rows + row] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
