@@ -484,23 +484,33 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
     const float scv = __ldg(sc + c), shv = __ldg(sh + c);
     const float mu = __ldg(mean + g * C + c), is = __ldg(istd + g * C + c);
     float s1 = 0.f, s2 = 0.f;
-    for (int pp = lane; pp < HWPRE; pp += 32) {
-      const float zv = __ldg(zg + c * HWPRE + pp);     // second read of z (L2-resident), instead of keeping it in smem
-      const float a = fmaf(zv, scv, shv);
-      float dv = 0.f;
-      if (POOL) {
-        const int yy = pp / SPRE, xx = pp - yy * SPRE;
-        if (yy < 2 * S && xx < 2 * S) {
-          const int cell = (yy >> 1) * S + (xx >> 1);
-          const int slot = ((yy & 1) << 1) | (xx & 1);
-          if (s_arg[c * HW + cell] == slot && a > 0.f) dv = s_D[c * HW + cell];
-        }
-      } else {
-        if (a > 0.f) dv = s_D[c * HW + pp];
+    if (POOL) {
+      // one lane per pooled cell: only the arg-max position of its 2x2 window receives gradient
+      for (int e = lane; e < 2 * SPRE - 1; e += 32) {      // row / column dropped by the floor pooling
+        const int idx = e < SPRE ? (SPRE - 1) * SPRE + e : (e - SPRE) * SPRE + (SPRE - 1);
+        da_out[c * HWPRE + idx] = 0.f;
       }
-      da_out[c * HWPRE + pp] = dv;
-      s1 += dv;
-      s2 = fmaf(dv, (zv - mu) * is, s2);
+      for (int cell = lane; cell < HW; cell += 32) {
+        const int cy = cell / S, cx = cell - cy * S;
+        const int base = c * HWPRE + (2 * cy) * SPRE + 2 * cx;
+        const int arg = s_arg[c * HW + cell];
+        const float zv = __ldg(zg + base + (arg >> 1) * SPRE + (arg & 1));
+        const float dv = fmaf(zv, scv, shv) > 0.f ? s_D[c * HW + cell] : 0.f;
+        da_out[base] = arg == 0 ? dv : 0.f;
+        da_out[base + 1] = arg == 1 ? dv : 0.f;
+        da_out[base + SPRE] = arg == 2 ? dv : 0.f;
+        da_out[base + SPRE + 1] = arg == 3 ? dv : 0.f;
+        s1 += dv;
+        s2 = fmaf(dv, (zv - mu) * is, s2);
+      }
+    } else {
+      for (int pp = lane; pp < HWPRE; pp += 32) {
+        const float zv = __ldg(zg + c * HWPRE + pp);     // second read of z (L2-resident), instead of keeping it in smem
+        const float dv = fmaf(zv, scv, shv) > 0.f ? s_D[c * HW + pp] : 0.f;
+        da_out[c * HWPRE + pp] = dv;
+        s1 += dv;
+        s2 = fmaf(dv, (zv - mu) * is, s2);
+      }
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
