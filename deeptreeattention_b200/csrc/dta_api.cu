@@ -28,6 +28,7 @@ struct dta_ctx {
   int conv_impl = 1;   // 1: tcgen05 split-bf16 implicit GEMM where built (conv1 forward + weight gradient), 0: fp32 SIMT
   long long launches = 0;
   int profile = 0;
+  int fuse_x = 1;      // conv1 forward converts the raw crops itself (no separate pack pass); 0 = pack kernel + pre-packed operand
   std::vector<std::string> stage_names;
   std::vector<double> stage_ms;
   std::vector<long long> stage_calls;
@@ -42,7 +43,6 @@ namespace {
 
 constexpr int kC[3] = {32, 64, 128};
 constexpr int kHWpre[3] = {121, 121, 25};   // conv output plane per block
-constexpr int kHWpost[3] = {121, 25, 4};    // after the block's max-pool
 constexpr int kAttRow[3] = {121, 64, 128};  // AttnCfg::ROW
 constexpr int kFeatLd[3] = {128, 256, 512};
 constexpr int kProwLd[3] = {AttnBwdRow<32, 11, false>::LD, AttnBwdRow<64, 11, true>::LD, AttnBwdRow<128, 5, true>::LD};
@@ -282,11 +282,14 @@ struct StageScope {
     span.t1 = take_event(c);
     cudaEventRecord(span.t0, st);
   }
-  ~StageScope() {
+  // Closes the bracket (idempotent): the destructor calls it, long stages call it early.
+  void end() {
     if (!on) return;
+    on = false;
     cudaEventRecord(span.t1, st);
     ctx->spans.push_back(span);
   }
+  ~StageScope() { end(); }
 };
 void fold_spans(dta_ctx* ctx) {
   for (ProfSpan& sp : ctx->spans) {
@@ -313,6 +316,14 @@ int fail(dta_ctx* ctx, int code, const std::string& msg) {
     if (e__ != cudaSuccess)                                                                \
       return fail(ctx, DTA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e__));  \
     (ctx)->launches++;                                                                     \
+  } while (0)
+
+// Same for the launch helpers that return the launch status.
+#define DTA_TC_CHECK(expr, what)                                                                          \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e__)); \
+    ctx->launches++;                                                                                      \
   } while (0)
 
 int check_shape(dta_ctx* ctx, const dta_shape* s, NetDesc* d) {
@@ -356,20 +367,20 @@ cudaError_t launch_wgrad(const ConvSrc& in, const ConvSrc& dz, float* part, int 
 }
 
 // ---- convolution launchers (conv_impl 1, tcgen05) ---------------------------------------
-template <int S, int NCO, bool ACC2>
+template <int S, int NCO, bool ACC2, bool FUSEX = false>
 cudaError_t run_tc_fprop(dta_ctx* ctx, cudaStream_t st, const __nv_bfloat16* xp, size_t rows, int nchunk, int chunks_per_group,
                          const __nv_bfloat16* wp, int nstage, Ptr2 bias, int bias_split, float* out, int out_ctot, int cout_g, int B,
-                         int G, float* stats = nullptr, int* nblk = nullptr) {
+                         int G, float* stats = nullptr, int* nblk = nullptr, FuseX fx = FuseX{nullptr, 0, nullptr}) {
   using Cfg = TcFprop<S, NCO, ACC2>;
-  auto kern = tc_conv_fprop_kernel<S, NCO, ACC2>;
+  auto kern = tc_conv_fprop_kernel<S, NCO, ACC2, FUSEX>;
   cudaError_t e = allow_smem(kern, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   const int ntiles = (int)((rows - 2 * kTcGuard) / Cfg::TILE);
   const int nwork = ntiles * G;
   const int grid = nwork < ctx->sm_count ? nwork : ctx->sm_count;
   if (nblk) *nblk = grid * 4;
-  kern<<<grid, kTcFpropThreads, Cfg::SMEM_BYTES, st>>>(xp, rows, nchunk, chunks_per_group, wp, nstage, bias, bias_split, out, out_ctot, cout_g,
-                                                       B, ntiles, G, stats);
+  kern<<<grid, kTcFpropThreads + (FUSEX ? 32 * kTcConvWarps : 0), Cfg::SMEM_BYTES, st>>>(xp, rows, nchunk, chunks_per_group, wp, nstage, bias,
+                                                                                         bias_split, out, out_ctot, cout_g, B, ntiles, G, stats, fx);
   return cudaGetLastError();
 }
 template <int S, class Cfg>
@@ -394,13 +405,6 @@ cudaError_t run_tc_pack(dta_ctx* ctx, cudaStream_t st, const ConvSrc& src, int G
   else tc_pack_stream_kernel<S, SRC_ACT, false><<<grid, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
   return cudaGetLastError();
 }
-int run_bn_stats(dta_ctx* ctx, cudaStream_t st, const float* z, int B, int ctot, int hw, float* stats) {
-  const int per = hw > 100 ? 8 : 16;
-  const int nblk = (B + per - 1) / per;
-  bn_partial_stats_kernel<<<dim3(nblk, (ctot + 7) / 8), 256, 0, st>>>(z, B, ctot, hw, per, stats);
-  return nblk;
-}
-
 ConvSrc src_raw(const float* x, int cin, int hw) {
   ConvSrc s{};
   s.mode = SRC_RAW; s.cin = cin; s.ctot = cin; s.src_hw = hw; s.a = x;
@@ -539,6 +543,10 @@ int dta_set_option(dta_ctx* ctx, const char* key, int64_t value) {
     ctx->profile = value != 0;
     return DTA_OK;
   }
+  if (!strcmp(key, "fuse_x")) {
+    ctx->fuse_x = value != 0;
+    return DTA_OK;
+  }
   return fail(ctx, DTA_ERR_INVALID_ARG, std::string("unknown option ") + key);
 }
 
@@ -584,8 +592,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   FwdWork W = layout_fwd(*shape, d, workspace);
 
   // 1. pack parameters into kernel-friendly tables (a few MB, once per step)
-  StageScope* pack_scope = new StageScope(ctx, "fwd.pack_params", st);
-  struct ScopeDrop { StageScope*& p; ~ScopeDrop() { delete p; p = nullptr; } } pack_drop{pack_scope};
+  StageScope pack_scope(ctx, "fwd.pack_params", st);
   for (int k = 0; k < 3 && ctx->conv_impl == 0; ++k) {
     Ptr2 w{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}};
     const int cin = k == 0 ? bands : kC[k - 1];
@@ -603,33 +610,39 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     }
   }
 
-  delete pack_scope; pack_scope = nullptr;
+  pack_scope.end();
   cudaError_t e;
   int nblk = 0;
   // 2. block 1: conv1 over the crops (both branches share the read of x)
   const bool tcp = ctx->conv_impl == 1;
   const TcGeom tg = tc_geom(B, bands, nb);
-#define DTA_TC_CHECK(expr, what)                                                                          \
-  do {                                                                                                    \
-    cudaError_t e__ = (expr);                                                                             \
-    if (e__ != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e__)); \
-    ctx->launches++;                                                                                      \
-  } while (0)
   auto conv_w = [&](int k) { return Ptr2{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}}; };
   auto conv_b = [&](int k) { return Ptr2{{params->branch[0].conv[k].conv_b, nb > 1 ? params->branch[1].conv[k].conv_b : nullptr}}; };
   if (tcp) {
     // tensor-core path: pack crops + weights, implicit GEMM, batch statistics of z
     {
       StageScope sc(ctx, "fwd.conv1_pack", st);
-      DTA_TC_CHECK(run_tc_pack<11>(ctx, st, src_raw(x, bands, kHW), 1, B, tg.nchunk1, tg.rows11, L.xp), "tc_pack_stream(x)");
+      if (!ctx->fuse_x) DTA_TC_CHECK(run_tc_pack<11>(ctx, st, src_raw(x, bands, kHW), 1, B, tg.nchunk1, tg.rows11, L.xp), "tc_pack_stream(x)");
       tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, st>>>(conv_w(0), nb, 32, bands, tg.nstage1, 0, W.wpf[0]);
       DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
     }
     {
       StageScope sc(ctx, "fwd.conv1", st);
-      DTA_TC_CHECK((run_tc_fprop<11, 64, false>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32, nb * 32, B, 1,
-                                               shape->training ? W.stats : nullptr, &nblk)),
-                   "tc_conv_fprop(conv1)");
+      if (ctx->fuse_x) {
+        // the crops are converted inside the convolution; the packed copy it leaves in L.xp feeds the weight gradient
+        if (2 * tg.nstage1 < tg.nchunk1) {   // chunks beyond the forward's K range (weight-gradient slice padding) stay zero
+          const size_t used = (size_t)2 * tg.nstage1 * tg.rows11 * 16, all = (size_t)tg.nchunk1 * tg.rows11 * 16;
+          cudaMemsetAsync(reinterpret_cast<char*>(L.xp) + used, 0, all - used, st);
+          cudaMemsetAsync(reinterpret_cast<char*>(L.xp) + all + used, 0, all - used, st);
+        }
+        DTA_TC_CHECK((run_tc_fprop<11, 64, false, true>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32,
+                                                       nb * 32, B, 1, shape->training ? W.stats : nullptr, &nblk, FuseX{x, bands, L.xp})),
+                     "tc_conv_fprop(conv1, fused crops)");
+      } else {
+        DTA_TC_CHECK((run_tc_fprop<11, 64, false>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32, nb * 32, B, 1,
+                                                 shape->training ? W.stats : nullptr, &nblk)),
+                     "tc_conv_fprop(conv1)");
+      }
     }
   } else {
     StageScope sc(ctx, "fwd.conv1", st);
@@ -862,8 +875,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   // upstream gradients per head (the alpha blend folds djoint into the two last heads)
   const float* dS[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int h = 0; h < d.n_heads; ++h) dS[h] = dscores[h];
-  StageScope* pre_scope = new StageScope(ctx, "bwd.prologue", st);
-  struct ScopeDrop { StageScope*& p; ~ScopeDrop() { delete p; p = nullptr; } } pre_drop{pre_scope};
+  StageScope pre_scope(ctx, "bwd.prologue", st);
   if (hang && djoint) {
     joint_bwd_kernel<<<(int)((nsc + 255) / 256), 256, 0, st>>>(dscores[2], dscores[5], djoint, params->alpha, W.dS[2], W.dS[5], nsc);
     DTA_CHECK_LAUNCH(ctx, "joint_bwd");
@@ -893,12 +905,6 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     }
     DTA_CHECK_LAUNCH(ctx, "pack_conv_wd");
   }
-#define DTA_TC_CHECK(expr, what)                                                                          \
-  do {                                                                                                    \
-    cudaError_t e__ = (expr);                                                                             \
-    if (e__ != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e__)); \
-    ctx->launches++;                                                                                      \
-  } while (0)
   if (dx) {
     Ptr2 w{{params->branch[0].conv[0].conv_w, nb > 1 ? params->branch[1].conv[0].conv_w : nullptr}};
     pack_conv_wd_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, 32, bands, 1, W.wd[0]);
@@ -922,7 +928,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     }
   }
 
-  delete pre_scope; pre_scope = nullptr;
+  pre_scope.end();
   auto bn_grads = [&](int k) {
     BnGrads g{};
     for (int b = 0; b < nb; ++b) {
@@ -1016,10 +1022,10 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     auto kern = attn_bwd_kernel<128, 5, true>;
     const size_t sm = attn_bwd_smem<128, 5, true>(classes);
     allow_smem(kern, sm);
-    StageScope* asc = new StageScope(ctx, "bwd.attn3", st);
+    StageScope asc(ctx, "bwd.attn3", st);
     kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], L.bn_mean[2], L.bn_istd[2], attn_prm(2), classes, L.att[2], L.feat[2],
                                               ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow[2]);
-    delete asc;
+    asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<3>");
     if ((rc = attn_param_grads(2)) != DTA_OK) return rc;
     if ((rc = bn_bwd(2)) != DTA_OK) return rc;
@@ -1050,10 +1056,10 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     auto kern = attn_bwd_kernel<64, 11, true>;
     const size_t sm = attn_bwd_smem<64, 11, true>(classes);
     allow_smem(kern, sm);
-    StageScope* asc = new StageScope(ctx, "bwd.attn2", st);
+    StageScope asc(ctx, "bwd.attn2", st);
     kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], L.bn_mean[1], L.bn_istd[1], attn_prm(1), classes, L.att[1], L.feat[1],
                                               ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow[1]);
-    delete asc;
+    asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<2>");
     if ((rc = attn_param_grads(1)) != DTA_OK) return rc;
     if ((rc = bn_bwd(1)) != DTA_OK) return rc;
@@ -1084,10 +1090,10 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     auto kern = attn_bwd_kernel<32, 11, false>;
     const size_t sm = attn_bwd_smem<32, 11, false>(classes);
     allow_smem(kern, sm);
-    StageScope* asc = new StageScope(ctx, "bwd.attn1", st);
+    StageScope asc(ctx, "bwd.attn1", st);
     kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], L.bn_mean[0], L.bn_istd[0], attn_prm(0), classes, L.att[0], L.feat[0],
                                               ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow[0]);
-    delete asc;
+    asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<1>");
     if ((rc = attn_param_grads(0)) != DTA_OK) return rc;
     if ((rc = bn_bwd(0)) != DTA_OK) return rc;

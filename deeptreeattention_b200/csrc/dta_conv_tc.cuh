@@ -218,12 +218,23 @@ struct TcFprop {
   static_assert(kTcGuard >= St::PT + 1, "guard must cover the largest tap shift");
 };
 
-template <int S, int NCO, bool ACC2>
-__global__ void __launch_bounds__(kTcFpropThreads, 1)
+// FUSEX (conv1): the A operand is not read pre-packed; eight extra "converter" warps read the raw fp32 crops, split them
+// into hi/lo bf16 straight into the shared-memory stage (generic-proxy stores + fence.proxy.async) and, when asked,
+// also emit the packed position stream to global memory for the weight-gradient kernel -- the separate pack pass over
+// the crops (183 MB read + 227 MB written) disappears into this kernel's shadow.
+constexpr int kTcConvWarps = 8;
+struct FuseX {
+  const float* x;             // crops (B, bands, S, S) float32
+  int bands;
+  __nv_bfloat16* xp_out;      // packed stream to write ([2][nchunk][rows][8]) or null
+};
+
+template <int S, int NCO, bool ACC2, bool FUSEX = false>
+__global__ void __launch_bounds__(kTcFpropThreads + (FUSEX ? 32 * kTcConvWarps : 0), 1)
 tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]*/, size_t rows, int nchunk, int chunks_per_group,
                      const __nv_bfloat16* __restrict__ wp /*[G][nstage][W_BYTES]*/, int nstage, Ptr2 bias, int bias_split,
                      float* __restrict__ out /*[B][out_ctot][S*S]*/, int out_ctot, int cout_g, int B, int ntiles, int G,
-                     float* __restrict__ stats /*[gridDim.x*4][out_ctot][2] or null: BatchNorm partial sums of out*/) {
+                     float* __restrict__ stats /*[gridDim.x*4][out_ctot][2] or null: BatchNorm partial sums of out*/, FuseX fx) {
   using Cfg = TcFprop<S, NCO, ACC2>;
   using St = Stream<S>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -238,7 +249,10 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
   const int nwork = ntiles * G;
 
   if (tid == 0) {
-    for (int i = 0; i < Cfg::NSTAGE; ++i) { tc::mbar_init(&full_bar[i], 1); tc::mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < Cfg::NSTAGE; ++i) {
+      tc::mbar_init(&full_bar[i], FUSEX ? 1 + 32 * kTcConvWarps : 1);   // W bulk copy (+ every converter thread)
+      tc::mbar_init(&empty_bar[i], 1);
+    }
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 8); }
     tc::mbar_fence_init();
   }
@@ -261,14 +275,16 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
           const uint32_t ph = (it / Cfg::NSTAGE) & 1;
           tc::mbar_wait(&empty_bar[st], ph ^ 1);
           unsigned char* sa = smem + (size_t)st * Cfg::STAGE_BYTES;
-          tc::mbar_arrive_expect_tx(&full_bar[st], Cfg::STAGE_BYTES);
+          tc::mbar_arrive_expect_tx(&full_bar[st], FUSEX ? Cfg::W_BYTES : Cfg::STAGE_BYTES);
+          if (!FUSEX) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int kc = 0; kc < 2; ++kc)
-              tc::bulk_g2s(sa + (size_t)(h * 2 + kc) * Cfg::AROWS * 16,
-                           xp + h * half_stride + ((size_t)(g * chunks_per_group + ks * 2 + kc) * rows + row0) * 8, Cfg::AROWS * 16,
-                           &full_bar[st]);
+              for (int kc = 0; kc < 2; ++kc)
+                tc::bulk_g2s(sa + (size_t)(h * 2 + kc) * Cfg::AROWS * 16,
+                             xp + h * half_stride + ((size_t)(g * chunks_per_group + ks * 2 + kc) * rows + row0) * 8, Cfg::AROWS * 16,
+                             &full_bar[st]);
+          }
           tc::bulk_g2s(sa + Cfg::A_BYTES, wp + ((size_t)g * nstage + ks) * (Cfg::W_BYTES / 2), Cfg::W_BYTES, &full_bar[st]);
         }
       }
@@ -315,7 +331,74 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
       if (leader) tc::mma_commit(&tmem_full[acc]);
       __syncwarp();
     }
-  } else {
+  } else if (FUSEX && warp >= 10) {
+    // ---------------- converters: fp32 crops -> split-bf16 A operand in shared memory (+ packed copy in global) ----------------
+    constexpr int NT = 32 * kTcConvWarps;
+    constexpr int UNITS = 2 * Cfg::AROWS;                       // (kchunk, row) pairs of 8 channels per stage
+    constexpr int PER = (UNITS + NT - 1) / NT;
+    const int ct = tid - kTcFpropThreads;
+    const size_t lo_off = (size_t)nchunk * rows;                // uint4 units between the hi and lo planes in global memory
+    uint4* xo = reinterpret_cast<uint4*>(fx.xp_out);
+    uint32_t it = 0;
+    for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+      const int tile = work;                                    // FUSEX runs with one group
+      const size_t row0 = (size_t)tile * Cfg::TILE;
+      for (int ks = 0; ks < nstage; ++ks, ++it) {
+        const int st = it % Cfg::NSTAGE;
+        const uint32_t ph = (it / Cfg::NSTAGE) & 1;
+        float v[PER][8];
+        // 1. all global loads of this thread's units first (the stage buffer is not needed yet)
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+          const int u = ct + k * NT;
+          const int kc = u / Cfg::AROWS, r = u - kc * Cfg::AROWS;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[k][j] = 0.f;
+          const long long q = (long long)row0 + r - kTcGuard;
+          if (u < UNITS && q >= 0 && q < (long long)B * St::PC) {
+            const int b = (int)(q / St::PC);
+            const int rr = (int)(q - (long long)b * St::PC);
+            const int yy = rr / St::PT, xx = rr - yy * St::PT;
+            const int ch0 = ks * 16 + kc * 8;
+            if (yy >= 1 && xx < S && ch0 < fx.bands) {
+              const float* src = fx.x + ((size_t)b * fx.bands + ch0) * (S * S) + (yy - 1) * S + xx;
+              const int nv = min(8, fx.bands - ch0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < nv) v[k][j] = __ldg(src + (size_t)j * (S * S));
+            }
+          }
+        }
+        // 2. the stage buffer must be free (MMAs that read its previous contents have completed)
+        tc::mbar_wait(&empty_bar[st], ph ^ 1);
+        uint4* sa = reinterpret_cast<uint4*>(smem + (size_t)st * Cfg::STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+          const int u = ct + k * NT;
+          if (u < UNITS) {
+            const int kc = u / Cfg::AROWS, r = u - kc * Cfg::AROWS;
+            uint4 hi, lo;
+            tc::split2(v[k][0], v[k][1], hi.x, lo.x);
+            tc::split2(v[k][2], v[k][3], hi.y, lo.y);
+            tc::split2(v[k][4], v[k][5], hi.z, lo.z);
+            tc::split2(v[k][6], v[k][7], hi.w, lo.w);
+            sa[kc * Cfg::AROWS + r] = hi;                              // [half 0][kc][AROWS]
+            sa[(2 + kc) * Cfg::AROWS + r] = lo;                        // [half 1][kc][AROWS]
+            // the tile's own rows go to the packed global copy; the first / last tile also own the stream's guard rows
+            const bool own = (r >= kTcGuard && r < kTcGuard + Cfg::TILE) || (tile == 0 && r < kTcGuard) ||
+                             (tile == ntiles - 1 && r >= kTcGuard + Cfg::TILE);
+            if (xo != nullptr && own) {
+              const size_t gi = (size_t)(ks * 2 + kc) * rows + row0 + r;
+              xo[gi] = hi;
+              xo[lo_off + gi] = lo;
+            }
+          }
+        }
+        tc::fence_async_smem();          // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        tc::mbar_arrive(&full_bar[st]);
+      }
+    }
+  } else if (warp < 10) {
     // ---------------- epilogue: TMEM -> registers -> out (NCHW fp32) ----------------
     const int ew = warp - 2;                   // 0..7
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -623,32 +706,6 @@ __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, int nspli
     const size_t q = flat / ptr_split;
     float* d = dw.p[q];
     if (d != nullptr) d[flat - q * ptr_split] = s;
-  }
-}
-
-// Per-channel sum / sum of squares of z[b][c][hw] over groups of crops (BatchNorm batch statistics
-// when the producing kernel has no statistics epilogue).  grid = (crop groups, ceil(C / 8)), 256 threads:
-// one warp per channel.  out[group][C][2].
-__global__ void bn_partial_stats_kernel(const float* __restrict__ z, int B, int C, int hw, int crops_per_group,
-                                        float* __restrict__ out) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.y * 8 + warp;
-  if (c >= C) return;
-  const int b0 = blockIdx.x * crops_per_group, b1 = min(B, b0 + crops_per_group);
-  float s = 0.f, q = 0.f;
-  for (int b = b0; b < b1; ++b) {
-    const float* p = z + ((size_t)b * C + c) * hw;
-    for (int i = lane; i < hw; i += 32) {
-      const float v = __ldg(p + i);
-      s += v;
-      q = fmaf(v, v, q);
-    }
-  }
-  s = warp_sum(s);
-  q = warp_sum(q);
-  if (lane == 0) {
-    out[((size_t)blockIdx.x * C + c) * 2 + 0] = s;
-    out[((size_t)blockIdx.x * C + c) * 2 + 1] = q;
   }
 }
 
