@@ -576,6 +576,8 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   int rc = check_shape(ctx, shape, &d);
   if (rc != DTA_OK) return rc;
   if (!x || !scores || !saved || !workspace) return fail(ctx, DTA_ERR_INVALID_ARG, "x, scores, saved and workspace are required");
+  if ((reinterpret_cast<uintptr_t>(saved) | reinterpret_cast<uintptr_t>(workspace)) & 255u)
+    return fail(ctx, DTA_ERR_INVALID_ARG, "saved and workspace must be 256-byte aligned (bulk copies and vector stores rely on it)");
   rc = validate_params(ctx, params, d, shape->net_kind, true);
   if (rc != DTA_OK) return rc;
   for (int h = 0; h < d.n_heads; ++h)
@@ -856,6 +858,8 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   int rc = check_shape(ctx, shape, &d);
   if (rc != DTA_OK) return rc;
   if (!x || !saved || !workspace || !grads || !dscores) return fail(ctx, DTA_ERR_INVALID_ARG, "x, saved, workspace, dscores and grads are required");
+  if ((reinterpret_cast<uintptr_t>(saved) | reinterpret_cast<uintptr_t>(workspace)) & 255u)
+    return fail(ctx, DTA_ERR_INVALID_ARG, "saved and workspace must be 256-byte aligned (bulk copies and vector stores rely on it)");
   rc = validate_params(ctx, params, d, shape->net_kind, false);
   if (rc != DTA_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);

@@ -14,6 +14,7 @@
  *    row-major, in the reference's own layouts (NCHW crops, state_dict() parameter shapes);
  *  - the caller owns every buffer (inputs, outputs, saved activations, workspace); the
  *    library allocates nothing per call and only ENQUEUES work on the given stream;
+ *    `saved` and `workspace` must be 256-byte aligned (any cudaMalloc / torch allocation is);
  *  - functions return DTA_OK (0) or a negative dta_status; dta_last_error() gives the text;
  *  - a dta_ctx belongs to one device and one host thread at a time (one per process rank).
  */

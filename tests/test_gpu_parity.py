@@ -261,3 +261,46 @@ def test_metadata_sensor_fusion_matches_torch_reference():
     out = m(x.cuda(), site.cuda())
     out.sum().backward()
     assert m.sensor_model.alpha.grad is not None and m.fc1.weight.grad is not None
+
+
+def test_wide_head_and_odd_sizes_match_oracle():
+    """More classes than one 32-wide reduction tile and than a warp, bands not a multiple of 8 or 16, odd batch."""
+    kind, bands, classes, batch = "hang2020", 21, 130, 7
+    table = orc.init_params(kind, bands, classes, 91, perturb_bn=True)
+    x, y = orc.make_inputs(batch, bands, classes, 91)
+    rloss, rres, rheads, rgrads, _ = orc.step(kind, table, x, y, regime="R2", training=True)
+    sens = gu.oracle_sensitivity(kind, table, x, y, "R2", True, rgrads, eps=1e-5, draws=2)
+    loss, res, heads, grads, _ = run_cuda(kind, bands, classes, table, x, y, "R2", True)
+    for h, rh in zip(heads, rheads):
+        np.testing.assert_allclose(h, rh.detach().numpy(), rtol=0, atol=SCORE_TOL)
+    for k, rg in rgrads.items():
+        if rg is None:
+            continue
+        err = float((grads[k].double() - rg.double()).abs().max())
+        assert err <= 1e-5 + 1e-3 * float(rg.abs().max()) + 8.0 * sens[k], k
+
+
+def test_large_batch_matches_oracle():
+    """B = 1536 crops (more than one wave of tiles, several weight-gradient stages per split) against the CPU oracle:
+    guards the index arithmetic at benchmark scale.  Gradient tolerance as above: 1e-3 of the tensor's scale plus the
+    oracle's own movement under a forward perturbation of the size of the split-bf16 rounding (ReLU / max-pool flips,
+    whose number grows with the batch)."""
+    kind, bands, classes, batch = "hang2020", 369, 50, 1536
+    table = orc.init_params(kind, bands, classes, 5, perturb_bn=True)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(batch, bands, 11, 11, generator=g)
+    y = torch.randint(0, classes, (batch,), generator=g)
+    rloss, rres, rheads, rgrads, rbufs = orc.step(kind, table, x, y, regime="R2", training=True)
+    sens = gu.oracle_sensitivity(kind, table, x, y, "R2", True, rgrads, eps=1e-5, draws=2)
+    loss, res, heads, grads, bufs = run_cuda(kind, bands, classes, table, x, y, "R2", True)
+    assert abs(loss - float(rloss)) < 1e-4
+    for h, rh in zip(heads, rheads):
+        np.testing.assert_allclose(h, rh.detach().numpy(), rtol=0, atol=2e-4)
+        assert_argmax(h, rh.detach().numpy())
+    for k, rb in rbufs.items():
+        np.testing.assert_allclose(bufs[k].numpy(), rb.numpy(), rtol=1e-5, atol=1e-5)
+    for k, rg in rgrads.items():
+        if rg is None:
+            continue
+        err = float((grads[k].double() - rg.double()).abs().max())
+        assert err <= 1e-6 + 1e-3 * float(rg.abs().max()) + 8.0 * sens[k], f"{k}: err {err:.3e} scale {float(rg.abs().max()):.3e} sens {sens[k]:.3e}"
