@@ -18,7 +18,7 @@ import torch
 from torch import nn
 from torch.nn import Module
 
-from . import _capi
+from . import _blocks, _capi
 
 _KIND_PREFIXES = {
     _capi.NET_HANG2020: ("spectral_network.", "spatial_network."),
@@ -237,15 +237,9 @@ class _FusedNet(Module):
 
 # ------------------------------------------------------------------- reference API surface
 def global_spectral_pool(x):
-    """Mean over H, W keeping a trailing singleton (reference Hang2020.py:7-12).  Host-side
-    helper only; inside the networks this is fused into the attention kernels."""
-    return torch.mean(x, dim=(2, 3)).unsqueeze(-1)
-
-
-def _block_only(name):
-    raise NotImplementedError(
-        f"{name}: stand-alone block forward is not built yet; use the network modules "
-        "(Hang2020 / spectral_network / spatial_network / vanilla_CNN), which run fused")
+    """Mean over H, W keeping a trailing singleton: (B, C, H, W) -> (B, C, 1) (reference Hang2020.py:7-12).
+    Stand-alone kernel (``dta_plane_mean``); inside the networks the squeeze is fused into the attention kernels."""
+    return _blocks.plane_mean(x)
 
 
 class conv_module(Module):
@@ -260,7 +254,9 @@ class conv_module(Module):
             self.max_pool = nn.MaxPool2d(maxpool_kernel)
 
     def forward(self, x, pool=False):
-        _block_only("conv_module")
+        """Stand-alone block forward (``dta_conv_module_forward``; any channel count / plane size).  The network
+        modules never call this: they run all their blocks fused."""
+        return _blocks.conv_module_forward(self, x, pool)
 
 
 class Classifier(Module):
@@ -271,7 +267,7 @@ class Classifier(Module):
         self.fc1 = nn.Linear(in_features=in_features, out_features=classes)
 
     def forward(self, features):
-        _block_only("Classifier")
+        return _blocks.classifier_forward(self, features)
 
 
 class spatial_attention(Module):
@@ -289,7 +285,8 @@ class spatial_attention(Module):
         self.class_pool = nn.MaxPool2d((pool, pool))
 
     def forward(self, x):
-        _block_only("spatial_attention")
+        """Returns (gated feature map, flattened class-pooled features) like the reference (:103-124)."""
+        return _blocks.attention_forward(self, _capi.ATTN_SPATIAL, x)
 
 
 class spectral_attention(Module):
@@ -305,7 +302,8 @@ class spectral_attention(Module):
         self.attention_conv2 = nn.Conv1d(filters, filters, kernel_size=kernel_size, padding="same")
 
     def forward(self, x):
-        _block_only("spectral_attention")
+        """Returns (gated feature map, pooled features) like the reference (:146-168)."""
+        return _blocks.attention_forward(self, _capi.ATTN_SPECTRAL, x)
 
 
 class _Branch(_FusedNet):

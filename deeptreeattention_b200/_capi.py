@@ -49,13 +49,28 @@ class Sizes(C.Structure):
                 ("n_heads", C.c_int32)]
 
 
+class Plane(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32)]
+
+
+class AdamHyper(C.Structure):
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("step", C.c_int64)]
+
+
+ATTN_SPECTRAL, ATTN_SPATIAL = 1, 2
+
+
 class StageTime(C.Structure):
     _fields_ = [("name", C.c_char * 40), ("total_ms", C.c_double), ("calls", C.c_int64)]
 
 
 EXPORTS = ["dta_abi_version", "dta_create", "dta_destroy", "dta_last_error", "dta_set_option", "dta_get_option",
            "dta_profile_read", "dta_query_sizes", "dta_forward", "dta_backward", "dta_loss_workspace_bytes",
-           "dta_cross_entropy_heads", "dta_preprocess_crops", "dta_grad_allreduce_sizes", "dta_grad_allreduce"]
+           "dta_cross_entropy_heads", "dta_preprocess_crops", "dta_grad_allreduce_sizes", "dta_grad_allreduce",
+           "dta_plane_mean", "dta_plane_mean_backward", "dta_conv_module_workspace_bytes", "dta_conv_module_forward",
+           "dta_conv_module_backward", "dta_attention_sizes", "dta_attention_forward", "dta_attention_backward",
+           "dta_classifier_forward", "dta_classifier_backward", "dta_adam_step"]
 
 
 def sources():
@@ -143,6 +158,22 @@ def lib():
         L.dta_grad_allreduce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p * 16), C.c_void_p, C.c_size_t, C.c_size_t,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
         L.dta_grad_allreduce.restype = C.c_int
+        vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
+        L.dta_plane_mean.argtypes = [vp, vp, sz, ci, vp, vp]
+        L.dta_plane_mean_backward.argtypes = [vp, vp, sz, ci, vp, vp]
+        L.dta_conv_module_workspace_bytes.argtypes = [C.POINTER(Plane), ci, C.POINTER(sz)]
+        L.dta_conv_module_forward.argtypes = [vp, C.POINTER(Plane), ci, ci, ci, ci, vp, C.POINTER(ConvBlock), vp, vp, vp, vp]
+        L.dta_conv_module_backward.argtypes = [vp, C.POINTER(Plane), ci, ci, ci, ci, vp, C.POINTER(ConvBlock), vp, vp, vp,
+                                               C.POINTER(ConvBlock), vp, vp, vp]
+        L.dta_attention_sizes.argtypes = [ci, C.POINTER(Plane), C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
+        L.dta_attention_forward.argtypes = [vp, ci, C.POINTER(Plane), vp, C.POINTER(Attention), vp, vp, vp, vp]
+        L.dta_attention_backward.argtypes = [vp, ci, C.POINTER(Plane), vp, C.POINTER(Attention), vp, vp, vp, vp,
+                                             C.POINTER(Attention), vp, vp]
+        L.dta_classifier_forward.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp]
+        L.dta_classifier_backward.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp]
+        L.dta_adam_step.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(AdamHyper), vp, vp, vp]
+        for name in EXPORTS[15:]:
+            getattr(L, name).restype = C.c_int
         _lib = L
         return L
 

@@ -119,7 +119,10 @@ const char* dta_last_error(const dta_ctx* ctx); /* ctx may be NULL: last create 
 /* Tuning / debugging knobs.  key "conv_impl": 0 = fp32 CUDA-core direct convolution,
  * 1 = tcgen05 split-bf16 implicit GEMM (default where implemented).
  * key "launches": read-only counter of kernels launched by the last forward/backward.
- * key "profile": 1 = record per-stage CUDA-event timings (see dta_profile_read). */
+ * key "profile": 1 = record per-stage CUDA-event timings (see dta_profile_read).
+ * key "overlap": 1 (default) = work off the critical path (parameter packing, weight gradients, small reductions) runs on a
+ * library-owned side stream, forked from and joined back to the caller's stream with events inside each call (still one
+ * stream-ordered call for the caller; a CUDA-graph capture records a DAG); 0 = everything on the caller's stream. */
 int dta_set_option(dta_ctx* ctx, const char* key, int64_t value);
 int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value);
 
@@ -212,6 +215,83 @@ int dta_grad_allreduce_sizes(size_t n_float4, size_t n_double, int world, size_t
                              size_t* scratch_bytes);
 int dta_grad_allreduce(dta_ctx* ctx, int rank, int world, void* const peer_buffers[], const void* multicast_buffer,
                        size_t n_float4, size_t n_double, void* scratch, void* sync_words, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stand-alone building blocks.  The reference's tests and notebooks call conv_module, spatial_attention,
+ * spectral_attention and Classifier on their own (tests/test_Hang2020.py:8-33); inside the networks they run fused
+ * (dta_forward).  These entry points cover ANY plane size / channel count with exact-fp32 CUDA-core kernels.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct dta_plane {
+  int32_t batch, channels, height, width; /* a (batch, channels, height, width) float32 NCHW tensor */
+} dta_plane;
+
+typedef enum dta_attention_kind {
+  DTA_ATTN_SPECTRAL = 1, /* Hang2020.spectral_attention (Hang2020.py:126-168) */
+  DTA_ATTN_SPATIAL = 2   /* Hang2020.spatial_attention  (Hang2020.py:68-124)  */
+} dta_attention_kind;
+
+/* global_spectral_pool (Hang2020.py:7-12): out[row] = mean over the hw positions of row `row` of `in`; rows = batch * channels.
+ * Backward: din[row][p] = dout[row] / hw. */
+int dta_plane_mean(dta_ctx* ctx, const float* in, size_t rows, int hw, float* out, void* cuda_stream);
+int dta_plane_mean_backward(dta_ctx* ctx, const float* dout, size_t rows, int hw, float* din, void* cuda_stream);
+
+/*
+ * conv_module.forward(x, pool) (Hang2020.py:24-31): Conv2d 3x3 "same" -> BatchNorm2d -> ReLU -> optional MaxPool2d.
+ *   in      : shape of x; `filters` output channels; pool_h = pool_w = 1 means no pooling (else kernel = stride, floor)
+ *   z       : (batch, filters, H, W)   convolution output, kept for backward
+ *   stat    : 2 * filters floats       BatchNorm mean | 1/sqrt(var + eps) used by this call, kept for backward
+ *   out     : (batch, filters, H / pool_h, W / pool_w)
+ * training != 0 uses batch statistics and updates params->bn_rm / bn_rv / bn_nbt like nn.BatchNorm2d.
+ * Backward: grads->conv_w, conv_b, bn_w, bn_b are overwritten (NULL entries skipped); dx may be NULL;
+ * workspace: dta_conv_module_workspace_bytes().
+ */
+int dta_conv_module_workspace_bytes(const dta_plane* in, int filters, size_t* out);
+int dta_conv_module_forward(dta_ctx* ctx, const dta_plane* in, int filters, int pool_h, int pool_w, int training, const float* x,
+                            const dta_conv_block* params, float* z, float* stat, float* out, void* cuda_stream);
+int dta_conv_module_backward(dta_ctx* ctx, const dta_plane* in, int filters, int pool_h, int pool_w, int training, const float* x,
+                             const dta_conv_block* params, const float* z, const float* stat, const float* dout,
+                             const dta_conv_block* grads, float* dx, void* workspace, void* cuda_stream);
+
+/*
+ * spectral_attention.forward / spatial_attention.forward (Hang2020.py:146-168 / 103-124): returns the gated map
+ * `out` (same shape as x) and the pooled head features `feat` (batch, feat_per_crop).  channels must be 32, 64 or 128
+ * (kernel sizes 3/5/7 resp. 7/5/3, class pool 4/2/1; DTA_ERR_UNSUPPORTED otherwise, the reference raises too).
+ *   saved : saved_floats_per_crop * batch floats kept for backward
+ * Backward: dout / dfeat are the upstream gradients of the two outputs (either may be NULL); dx may be NULL;
+ * grads uses the dta_attention layout of `params` (NULL entries skipped; Conv1d off-centre taps are written as exact zeros).
+ */
+int dta_attention_sizes(int kind, const dta_plane* in, size_t* feat_per_crop, size_t* saved_floats_per_crop, size_t* workspace_bytes);
+int dta_attention_forward(dta_ctx* ctx, int kind, const dta_plane* in, const float* x, const dta_attention* params, float* out,
+                          float* feat, float* saved, void* cuda_stream);
+int dta_attention_backward(dta_ctx* ctx, int kind, const dta_plane* in, const float* x, const dta_attention* params, const float* saved,
+                           const float* dout, const float* dfeat, float* dx, const dta_attention* grads, void* workspace,
+                           void* cuda_stream);
+
+/* Classifier.forward (Hang2020.py:63-66): scores = feat W^T + b.  Backward: dfeat (may be NULL), dw, db (may be NULL). */
+int dta_classifier_forward(dta_ctx* ctx, int batch, int in_features, int classes, const float* feat, const float* w, const float* b,
+                           float* scores, void* cuda_stream);
+int dta_classifier_backward(dta_ctx* ctx, int batch, int in_features, int classes, const float* feat, const float* w,
+                            const float* dscores, float* dfeat, float* dw, float* db, void* cuda_stream);
+
+/*
+ * Fused Adam step over a table of parameter tensors: ONE kernel launch for the whole model.  Replaces the optimizer the reference
+ * configures around the path, torch.optim.Adam(self.model.parameters(), lr=config["lr"]) (src/main.py:135-136,
+ * src/models/multi_stage.py:258-262): betas / eps / weight_decay as in torch (L2 form), no amsgrad.
+ *   params[i], grads[i] : n_tensors float32 tensors of numel[i] elements (n_tensors <= 96); tensors whose gradient is None are
+ *                         simply left out of the table, as torch skips them
+ *   exp_avg, exp_avg_sq : flat float32 moment buffers; tensor i occupies [offset[i], offset[i] + numel[i])
+ *   param64 / grad64 / moments64 : the one float64 parameter of the path (Hang2020.alpha) with its 2 moments, or NULL
+ *   step         : 1-based step number (host value) -- or step_device != NULL: an int64 device counter that the call
+ *                  increments first and then reads, and lr_device (may be NULL) a float32 device scalar overriding h->lr, so
+ *                  that a captured CUDA graph replays correct bias corrections and a scheduler can change lr without re-capture
+ */
+typedef struct dta_adam_hyper {
+  double lr, beta1, beta2, eps, weight_decay;
+  int64_t step;
+} dta_adam_hyper;
+int dta_adam_step(dta_ctx* ctx, int n_tensors, float* const params[], const float* const grads[], const int64_t numel[],
+                  const int64_t offset[], float* exp_avg, float* exp_avg_sq, double* param64, const double* grad64,
+                  double* moments64, const dta_adam_hyper* h, int64_t* step_device, const float* lr_device, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -75,7 +75,8 @@ def test_reference_api_surface_and_errors(tmp_path):
         H.spectral_attention(filters=48)
     with pytest.raises(ValueError):
         H.spatial_attention(filters=48)
-    assert H.global_spectral_pool(torch.ones(2, 3, 4, 4)).shape == (2, 3, 1)
+    with pytest.raises(RuntimeError):
+        H.global_spectral_pool(torch.ones(2, 3, 4, 4))     # no CPU path for the helper either
     m = H.Hang2020(bands=3, classes=10)
     with pytest.raises(RuntimeError):
         m(torch.randn(2, 3, 11, 11))          # no CPU path, must not silently fall back
