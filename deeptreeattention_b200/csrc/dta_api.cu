@@ -190,7 +190,8 @@ struct BwdWork {
   float* prow[3];   // per-crop partial parameter gradients of each attention block
   float* wpart;
   float* wd[3];
-  __nv_bfloat16* dzp;      // split-bf16 position stream of the current block's conv-output gradient
+  __nv_bfloat16* dzp[3];   // split-bf16 position streams of each block's conv-output gradient (one per block: block k's weight
+                           // gradient may still read its stream on the side stream while block k-1's is being packed)
   __nv_bfloat16* wdp[2];   // packed input-gradient weights of conv2, conv3 (tensor-core path)
   float* rpart;            // partial tiles of the batched small-gradient reduction
   size_t bytes;
@@ -217,10 +218,9 @@ BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
   for (int k = 0; k < 3; ++k)
     if (wp_tc[k] > wp) wp = wp_tc[k];
   W.wpart = c.take(wp);
-  size_t dz16 = (size_t)2 * 8 * tg.rows11;                                     // conv1: 64 merged channels
-  if ((size_t)2 * d.nb * 8 * tg.rows11 > dz16) dz16 = (size_t)2 * d.nb * 8 * tg.rows11;   // conv2: 64 per branch
-  if ((size_t)2 * d.nb * 16 * tg.rows5 > dz16) dz16 = (size_t)2 * d.nb * 16 * tg.rows5;   // conv3: 128 per branch
-  W.dzp = take_bf16(c, dz16);
+  W.dzp[0] = take_bf16(c, (size_t)2 * 8 * tg.rows11);           // conv1: 64 merged channels
+  W.dzp[1] = take_bf16(c, (size_t)2 * d.nb * 8 * tg.rows11);    // conv2: 64 per branch
+  W.dzp[2] = take_bf16(c, (size_t)2 * d.nb * 16 * tg.rows5);    // conv3: 128 per branch
   W.wdp[0] = take_bf16(c, (size_t)d.nb * 4 * (TcFprop<11, 32, true>::W_BYTES / 16));
   W.wdp[1] = take_bf16(c, (size_t)d.nb * 8 * (TcFprop<5, 64, true>::W_BYTES / 16));
   W.rpart = c.take((size_t)reduce_tiles_bound(s.classes, d.nb) * kReduceSplits * 1024);
@@ -407,6 +407,22 @@ int dta_create(dta_ctx** out, int device) {
   dta_ctx* c = new dta_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  // side stream (highest priority: its one-CTA-per-SM tensor kernels must get their shared memory before a co-scheduled
+  // attention grid fills the SMs) and the events that fork / join it
+  {
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(device);
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi) != cudaSuccess) c->side = nullptr;
+    for (int i = 0; i < 32 && c->side; ++i) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) c->sync_events.push_back(e);
+    }
+    cudaGetLastError();
+    cudaSetDevice(prev);
+  }
   *out = c;
   return DTA_OK;
 }
@@ -415,6 +431,8 @@ void dta_destroy(dta_ctx* ctx) {
   if (!ctx) return;
   fold_spans(ctx);
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->sync_events) cudaEventDestroy(e);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
   delete ctx;
 }
 
@@ -452,6 +470,10 @@ int dta_set_option(dta_ctx* ctx, const char* key, int64_t value) {
     ctx->fuse_x = value != 0;
     return DTA_OK;
   }
+  if (!strcmp(key, "overlap")) {
+    ctx->overlap = value != 0;
+    return DTA_OK;
+  }
   return fail(ctx, DTA_ERR_INVALID_ARG, std::string("unknown option ") + key);
 }
 
@@ -461,6 +483,8 @@ int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value) {
   if (!strcmp(key, "launches")) { *value = ctx->launches; return DTA_OK; }
   if (!strcmp(key, "profile")) { *value = ctx->profile; return DTA_OK; }
   if (!strcmp(key, "sm_count")) { *value = ctx->sm_count; return DTA_OK; }
+  if (!strcmp(key, "overlap")) { *value = ctx->overlap; return DTA_OK; }
+  if (!strcmp(key, "fuse_x")) { *value = ctx->fuse_x; return DTA_OK; }
   return DTA_ERR_INVALID_ARG;
 }
 
@@ -498,7 +522,14 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   SavedLayout L = layout_saved(*shape, d, saved);
   FwdWork W = layout_fwd(*shape, d, workspace);
 
-  // 1. pack parameters into kernel-friendly tables (a few MB, once per step)
+  // 1. pack parameters into kernel-friendly tables (a few MB, once per step).  Everything that depends on the parameters
+  //    only (attention tables, conv2/conv3 operand tables, guard rows of the activation streams) goes to the side stream and
+  //    runs under conv1; it is joined before the first consumer (block 1's attention kernel).
+  SideStream side(ctx, st);
+  side.wait_main();
+  cudaStream_t ss = side.stream();
+  const bool tcp = ctx->conv_impl == 1;
+  const TcGeom tg = tc_geom(shape->batch, shape->bands, d.nb);
   StageScope pack_scope(ctx, "fwd.pack_params", st);
   for (int k = 0; k < 3 && ctx->conv_impl == 0; ++k) {
     Ptr2 w{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}};
@@ -510,10 +541,24 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     if (d.btype[g] != BR_SPECTRAL) continue;
     for (int k = 0; k < 3; ++k) {
       const int ks = k == 0 ? 3 : (k == 1 ? 5 : 7);  // Hang2020.py:136-141
-      pack_spectral_kernel<<<(kC[k] * kC[k] + 255) / 256, 256, 0, st>>>(params->branch[g].attn[k].w0, kC[k], ks, L.spec_pack[g][k][0], L.spec_pack[g][k][1]);
+      pack_spectral_kernel<<<(kC[k] * kC[k] + 255) / 256, 256, 0, ss>>>(params->branch[g].attn[k].w0, kC[k], ks, L.spec_pack[g][k][0], L.spec_pack[g][k][1]);
       DTA_CHECK_LAUNCH(ctx, "pack_spectral");
-      pack_spectral_kernel<<<(kC[k] * kC[k] + 255) / 256, 256, 0, st>>>(params->branch[g].attn[k].w1, kC[k], ks, L.spec_pack[g][k][2], L.spec_pack[g][k][3]);
+      pack_spectral_kernel<<<(kC[k] * kC[k] + 255) / 256, 256, 0, ss>>>(params->branch[g].attn[k].w1, kC[k], ks, L.spec_pack[g][k][2], L.spec_pack[g][k][3]);
       DTA_CHECK_LAUNCH(ctx, "pack_spectral");
+    }
+  }
+  auto conv_w = [&](int k) { return Ptr2{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}}; };
+  auto conv_b = [&](int k) { return Ptr2{{params->branch[0].conv[k].conv_b, nb > 1 ? params->branch[1].conv[k].conv_b : nullptr}}; };
+  if (tcp) {
+    tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, ss>>>(conv_w(1), nb, 64, 32, 2, 1, W.wpf[1]);
+    DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
+    tc_pack_w_fprop_kernel<128><<<ctx->sm_count, 256, 0, ss>>>(conv_w(2), nb, 128, 64, 4, 1, W.wpf[2]);
+    DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
+    if (!vanilla) {   // the attention kernels write the crop rows of a1p / a2p; the guard and tail rows are zeroed here
+      tc_zero_guards_kernel<<<32, 256, 0, ss>>>(L.a1p, tg.rows11, nb * 4, (size_t)B * Stream<11>::PC);
+      DTA_CHECK_LAUNCH(ctx, "tc_zero_guards");
+      tc_zero_guards_kernel<<<32, 256, 0, ss>>>(L.a2p, tg.rows5, nb * 8, (size_t)B * Stream<5>::PC);
+      DTA_CHECK_LAUNCH(ctx, "tc_zero_guards");
     }
   }
 
@@ -521,10 +566,6 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   cudaError_t e;
   int nblk = 0;
   // 2. block 1: conv1 over the crops (both branches share the read of x)
-  const bool tcp = ctx->conv_impl == 1;
-  const TcGeom tg = tc_geom(B, bands, nb);
-  auto conv_w = [&](int k) { return Ptr2{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}}; };
-  auto conv_b = [&](int k) { return Ptr2{{params->branch[0].conv[k].conv_b, nb > 1 ? params->branch[1].conv[k].conv_b : nullptr}}; };
   if (tcp) {
     // tensor-core path: pack crops + weights, implicit GEMM, batch statistics of z
     {
@@ -576,6 +617,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     return m;
   };
   if ((rc = bn_finalize(0, nblk)) != DTA_OK) return rc;
+  side.join();   // parameter tables are ready from here on
   if (!vanilla) {
     StageScope sc(ctx, "fwd.attn1", st);
     auto kern = attn_fwd_kernel<32, 11, false>;
@@ -590,14 +632,8 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     ConvSrc src = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
     {
       StageScope sc(ctx, "fwd.conv2_pack", st);
-      if (vanilla) {
-        DTA_TC_CHECK(run_tc_pack<11>(ctx, st, src, nb, B, nb * 4, tg.rows11, L.a1p), "tc_pack_stream(act1)");
-      } else {   // block 1's attention kernel already wrote the crop rows of a1p
-        tc_zero_guards_kernel<<<32, 256, 0, st>>>(L.a1p, tg.rows11, nb * 4, (size_t)B * Stream<11>::PC);
-        DTA_CHECK_LAUNCH(ctx, "tc_zero_guards");
-      }
-      tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, st>>>(conv_w(1), nb, 64, 32, 2, 1, W.wpf[1]);
-      DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
+      // block 1's attention kernel already wrote the crop rows of a1p (vanilla_CNN has no attention kernel: pack here)
+      if (vanilla) DTA_TC_CHECK(run_tc_pack<11>(ctx, st, src, nb, B, nb * 4, tg.rows11, L.a1p), "tc_pack_stream(act1)");
     }
     {
       StageScope sc(ctx, "fwd.conv2", st);
@@ -627,14 +663,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     ConvSrc src = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
     {
       StageScope sc(ctx, "fwd.conv3_pack", st);
-      if (vanilla) {
-        DTA_TC_CHECK(run_tc_pack<5>(ctx, st, src, nb, B, nb * 8, tg.rows5, L.a2p), "tc_pack_stream(act2)");
-      } else {
-        tc_zero_guards_kernel<<<32, 256, 0, st>>>(L.a2p, tg.rows5, nb * 8, (size_t)B * Stream<5>::PC);
-        DTA_CHECK_LAUNCH(ctx, "tc_zero_guards");
-      }
-      tc_pack_w_fprop_kernel<128><<<ctx->sm_count, 256, 0, st>>>(conv_w(2), nb, 128, 64, 4, 1, W.wpf[2]);
-      DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
+      if (vanilla) DTA_TC_CHECK(run_tc_pack<5>(ctx, st, src, nb, B, nb * 8, tg.rows5, L.a2p), "tc_pack_stream(act2)");
     }
     {
       StageScope sc(ctx, "fwd.conv3", st);
@@ -781,6 +810,13 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   const size_t nsc = (size_t)B * classes;
   cudaError_t e;
 
+  // Side stream: everything off the critical path dgrad -> attention backward -> BatchNorm backward -> pack runs there:
+  // parameter packing and gradient zero-fill first, then each block's weight gradient (+ split-K reduce) under the NEXT
+  // block's attention backward, the batched small-parameter reduction under conv1's weight gradient.
+  SideStream side(ctx, st);
+  side.wait_main();
+  cudaStream_t ss = side.stream();
+
   // upstream gradients per head (the alpha blend folds djoint into the two last heads)
   const float* dS[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   for (int h = 0; h < d.n_heads; ++h) dS[h] = dscores[h];
@@ -807,10 +843,10 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   for (int k = 1; k < 3; ++k) {
     Ptr2 w{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}};
     if (tcp) {
-      if (k == 1) tc_pack_w_fprop_kernel<32><<<ctx->sm_count, 256, 0, st>>>(w, nb, 64, 32, 4, 2, W.wdp[0]);
-      else tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, st>>>(w, nb, 128, 64, 8, 2, W.wdp[1]);
+      if (k == 1) tc_pack_w_fprop_kernel<32><<<ctx->sm_count, 256, 0, ss>>>(w, nb, 64, 32, 4, 2, W.wdp[0]);
+      else tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, ss>>>(w, nb, 128, 64, 8, 2, W.wdp[1]);
     } else {
-      pack_conv_wd_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, kC[k], kC[k - 1], 0, W.wd[k]);
+      pack_conv_wd_kernel<<<ctx->sm_count * 2, 256, 0, ss>>>(w, nb, kC[k], kC[k - 1], 0, W.wd[k]);
     }
     DTA_CHECK_LAUNCH(ctx, "pack_conv_wd");
   }
@@ -826,13 +862,13 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     for (int k = 0; k < 3; ++k) {
       if (d.btype[g] == BR_SPECTRAL) {
         const int ks = k == 0 ? 3 : (k == 1 ? 5 : 7);
-        if (gb.attn[k].w0) cudaMemsetAsync(gb.attn[k].w0, 0, sizeof(float) * kC[k] * kC[k] * ks, st);
-        if (gb.attn[k].w1) cudaMemsetAsync(gb.attn[k].w1, 0, sizeof(float) * kC[k] * kC[k] * ks, st);
+        if (gb.attn[k].w0) cudaMemsetAsync(gb.attn[k].w0, 0, sizeof(float) * kC[k] * kC[k] * ks, ss);
+        if (gb.attn[k].w1) cudaMemsetAsync(gb.attn[k].w1, 0, sizeof(float) * kC[k] * kC[k] * ks, ss);
       }
       const int F = d.btype[g] == BR_SPECTRAL ? kC[k] : (d.btype[g] == BR_SPATIAL ? 4 * kC[k] : 512);
       if (head_ds(g, k) == nullptr) {
-        if (gb.fc_w[k]) cudaMemsetAsync(gb.fc_w[k], 0, sizeof(float) * classes * F, st);
-        if (gb.fc_b[k]) cudaMemsetAsync(gb.fc_b[k], 0, sizeof(float) * classes, st);
+        if (gb.fc_w[k]) cudaMemsetAsync(gb.fc_w[k], 0, sizeof(float) * classes * F, ss);
+        if (gb.fc_b[k]) cudaMemsetAsync(gb.fc_b[k], 0, sizeof(float) * classes, ss);
       }
     }
   }
@@ -912,16 +948,16 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     for (int g = 0; g < nb; ++g) p.p[g] = head_ds(g, k);
     return p;
   };
-  auto reduce_w = [&](int k, int cin, int nsplit) -> int {
-    StageScope sc(ctx, "bwd.wgrad_reduce", st);
+  auto reduce_w = [&](int k, int cin, int nsplit) -> int {   // on the side stream, right behind the weight gradient it reduces
+    StageScope sc(ctx, "bwd.wgrad_reduce", ss);
     MutPtr2 dw{{grads->branch[0].conv[k].conv_w, nb > 1 ? grads->branch[1].conv[k].conv_w : nullptr}};
     const size_t per_branch = (size_t)kC[k] * cin * 9;
     if (tcp) {
       // tensor-core partials are [split][g][tap][ci][co]; conv1 is one group over both branches' output channels
       const int G = k == 0 ? 1 : nb, cout_g = k == 0 ? nb * kC[0] : kC[k];
-      tc_wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W.wpart, nsplit, G, cout_g, cin, dw, per_branch);
+      tc_wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, ss>>>(W.wpart, nsplit, G, cout_g, cin, dw, per_branch);
     } else
-    wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(W.wpart, nsplit, 1, per_branch * nb, dw, per_branch);
+    wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, ss>>>(W.wpart, nsplit, 1, per_branch * nb, dw, per_branch);
     DTA_CHECK_LAUNCH(ctx, "wgrad_reduce");
     return DTA_OK;
   };
@@ -940,24 +976,29 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     if ((rc = bn_bwd(2)) != DTA_OK) return rc;
     ConvSrc dz = src_dz(W.da[2], L.z[2], 128, nb * 128, 25, W.k0[2], W.k1[2], W.k2[2]);
     ConvSrc in = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
+    side.join();   // packed input-gradient weights (and the gradient zero-fill) are done
     if (tcp) {
-      { StageScope sc(ctx, "bwd.conv3_pack", st); DTA_TC_CHECK(run_tc_pack<5>(ctx, st, dz, nb, B, nb * 16, tg.rows5, W.dzp), "tc_pack_stream(dz3)"); }
+      { StageScope sc(ctx, "bwd.conv3_pack", st); DTA_TC_CHECK(run_tc_pack<5>(ctx, st, dz, nb, B, nb * 16, tg.rows5, W.dzp[2]), "tc_pack_stream(dz3)"); }
       {
-        StageScope sc(ctx, "bwd.conv3_wgrad", st);
-        DTA_TC_CHECK((run_tc_wgrad<5, WgradCfg3>(st, W.dzp, nb * 16, L.a2p, nb * 8, tg.rows5, 64, 128, nb, tg.w3, W.wpart)), "tc_conv_wgrad(conv3)");
+        StageScope sc(ctx, "bwd.conv3_dgrad", st);
+        DTA_TC_CHECK((run_tc_fprop<5, 64, true>(ctx, st, W.dzp[2], tg.rows5, nb * 16, 16, W.wdp[1], 8, Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, 64, B, nb)),
+                     "tc_conv_fprop(conv3 dgrad)");
+      }
+      side.wait_main();   // the weight gradient starts when the input gradient has finished, next to block 2's attention backward
+      {
+        StageScope sc(ctx, "bwd.conv3_wgrad", ss);
+        DTA_TC_CHECK((run_tc_wgrad<5, WgradCfg3>(ss, W.dzp[2], nb * 16, L.a2p, nb * 8, tg.rows5, 64, 128, nb, tg.w3, W.wpart)), "tc_conv_wgrad(conv3)");
       }
       if ((rc = reduce_w(2, 64, tg.w3.nsplit)) != DTA_OK) return rc;
-      StageScope sc(ctx, "bwd.conv3_dgrad", st);
-      DTA_TC_CHECK((run_tc_fprop<5, 64, true>(ctx, st, W.dzp, tg.rows5, nb * 16, 16, W.wdp[1], 8, Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, 64, B, nb)),
-                   "tc_conv_fprop(conv3 dgrad)");
     } else {
-      { StageScope sc(ctx, "bwd.conv3_wgrad", st); e = launch_wgrad<5, 32, 128, 8>(in, dz, W.wpart, B, sp.n[2], sp.per[2], nb, st); }
-      if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 wgrad: ") + cudaGetErrorString(e));
-      ctx->launches++;
-      if ((rc = reduce_w(2, 64, sp.n[2])) != DTA_OK) return rc;
       { StageScope sc(ctx, "bwd.conv3_dgrad", st); e = launch_fprop<5, 4, 4, 8, 64, 8>(dz, W.wd[2], Ptr2{{nullptr, nullptr}}, 64, W.dout[1], nb * 64, nullptr, B, nb, st, nullptr); }
       if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 dgrad: ") + cudaGetErrorString(e));
       ctx->launches++;
+      side.wait_main();
+      { StageScope sc(ctx, "bwd.conv3_wgrad", ss); e = launch_wgrad<5, 32, 128, 8>(in, dz, W.wpart, B, sp.n[2], sp.per[2], nb, ss); }
+      if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv3 wgrad: ") + cudaGetErrorString(e));
+      ctx->launches++;
+      if ((rc = reduce_w(2, 64, sp.n[2])) != DTA_OK) return rc;
     }
   }
   // ---- block 2 ----
@@ -975,23 +1016,27 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     ConvSrc dz = src_dz(W.da[1], L.z[1], 64, nb * 64, 121, W.k0[1], W.k1[1], W.k2[1]);
     ConvSrc in = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
     if (tcp) {
-      { StageScope sc(ctx, "bwd.conv2_pack", st); DTA_TC_CHECK(run_tc_pack<11>(ctx, st, dz, nb, B, nb * 8, tg.rows11, W.dzp), "tc_pack_stream(dz2)"); }
+      { StageScope sc(ctx, "bwd.conv2_pack", st); DTA_TC_CHECK(run_tc_pack<11>(ctx, st, dz, nb, B, nb * 8, tg.rows11, W.dzp[1]), "tc_pack_stream(dz2)"); }
       {
-        StageScope sc(ctx, "bwd.conv2_wgrad", st);
-        DTA_TC_CHECK((run_tc_wgrad<11, WgradCfg2>(st, W.dzp, nb * 8, L.a1p, nb * 4, tg.rows11, 32, 64, nb, tg.w2, W.wpart)), "tc_conv_wgrad(conv2)");
+        StageScope sc(ctx, "bwd.conv2_dgrad", st);
+        DTA_TC_CHECK((run_tc_fprop<11, 32, true>(ctx, st, W.dzp[1], tg.rows11, nb * 8, 8, W.wdp[0], 4, Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, 32, B, nb)),
+                     "tc_conv_fprop(conv2 dgrad)");
+      }
+      side.wait_main();   // next to block 1's attention backward
+      {
+        StageScope sc(ctx, "bwd.conv2_wgrad", ss);
+        DTA_TC_CHECK((run_tc_wgrad<11, WgradCfg2>(ss, W.dzp[1], nb * 8, L.a1p, nb * 4, tg.rows11, 32, 64, nb, tg.w2, W.wpart)), "tc_conv_wgrad(conv2)");
       }
       if ((rc = reduce_w(1, 32, tg.w2.nsplit)) != DTA_OK) return rc;
-      StageScope sc(ctx, "bwd.conv2_dgrad", st);
-      DTA_TC_CHECK((run_tc_fprop<11, 32, true>(ctx, st, W.dzp, tg.rows11, nb * 8, 8, W.wdp[0], 4, Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, 32, B, nb)),
-                   "tc_conv_fprop(conv2 dgrad)");
     } else {
-      { StageScope sc(ctx, "bwd.conv2_wgrad", st); e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[1], sp.per[1], nb, st); }
-      if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 wgrad: ") + cudaGetErrorString(e));
-      ctx->launches++;
-      if ((rc = reduce_w(1, 32, sp.n[1])) != DTA_OK) return rc;
       { StageScope sc(ctx, "bwd.conv2_dgrad", st); e = launch_fprop<11, 1, 8, 4, 32, 16>(dz, W.wd[1], Ptr2{{nullptr, nullptr}}, 32, W.dout[0], nb * 32, nullptr, B, nb, st, nullptr); }
       if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 dgrad: ") + cudaGetErrorString(e));
       ctx->launches++;
+      side.wait_main();
+      { StageScope sc(ctx, "bwd.conv2_wgrad", ss); e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[1], sp.per[1], nb, ss); }
+      if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv2 wgrad: ") + cudaGetErrorString(e));
+      ctx->launches++;
+      if ((rc = reduce_w(1, 32, sp.n[1])) != DTA_OK) return rc;
     }
   }
   // ---- block 1 ----
@@ -1005,33 +1050,39 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<1>");
     if ((rc = attn_param_grads(0)) != DTA_OK) return rc;
+    // every attention block has left its per-crop partials: ONE batched reduction for all small parameter gradients, on the
+    // side stream (under BatchNorm backward / pack / conv1's weight gradient)
+    if (rtiles > 0) {
+      side.wait_main();
+      StageScope sc(ctx, "bwd.small_param_grads", ss);
+      if (rtiles > reduce_tiles_bound(classes, nb)) return fail(ctx, DTA_ERR_UNSUPPORTED, "reduction tile bound exceeded");
+      batched_reduce_kernel<<<dim3(rtiles, kReduceSplits), 256, 0, ss>>>(rtab, B, W.rpart);
+      DTA_CHECK_LAUNCH(ctx, "batched_reduce");
+      batched_reduce_finish_kernel<<<rtiles, 256, 0, ss>>>(rtab, W.rpart);
+      DTA_CHECK_LAUNCH(ctx, "batched_reduce_finish");
+    }
     if ((rc = bn_bwd(0)) != DTA_OK) return rc;
     ConvSrc dz = src_dz(W.da[0], L.z[0], nb * 32, nb * 32, 121, W.k0[0], W.k1[0], W.k2[0]);
     ConvSrc in = src_raw(x, bands, kHW);
     int conv1_nsplit = sp.n[0];
     if (tcp) {
-      { StageScope sc(ctx, "bwd.conv1_pack", st); DTA_TC_CHECK(run_tc_pack<11>(ctx, st, dz, 1, B, 8, tg.rows11, W.dzp), "tc_pack_stream(dz1)"); }
-      StageScope sc(ctx, "bwd.conv1_wgrad", st);
-      e = run_tc_wgrad<11, WgradCfg1>(st, W.dzp, 8, L.xp, tg.nchunk1, tg.rows11, bands, nb * 32, 1, tg.w1, W.wpart);
+      { StageScope sc(ctx, "bwd.conv1_pack", st); DTA_TC_CHECK(run_tc_pack<11>(ctx, st, dz, 1, B, 8, tg.rows11, W.dzp[0]), "tc_pack_stream(dz1)"); }
+      side.wait_main();   // the split-K partial buffer is shared with conv2's weight gradient: stay behind it on the side stream
+      StageScope sc(ctx, "bwd.conv1_wgrad", ss);
+      e = run_tc_wgrad<11, WgradCfg1>(ss, W.dzp[0], 8, L.xp, tg.nchunk1, tg.rows11, bands, nb * 32, 1, tg.w1, W.wpart);
       conv1_nsplit = tg.w1.nsplit;
     } else {
-      StageScope sc(ctx, "bwd.conv1_wgrad", st);
-      if (nb == 2) e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
-      else e = launch_wgrad<11, 32, 32, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, st);
+      side.wait_main();
+      StageScope sc(ctx, "bwd.conv1_wgrad", ss);
+      if (nb == 2) e = launch_wgrad<11, 32, 64, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, ss);
+      else e = launch_wgrad<11, 32, 32, 8>(in, dz, W.wpart, B, sp.n[0], sp.per[0], 1, ss);
     }
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv1 wgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
     if ((rc = reduce_w(0, bands, conv1_nsplit)) != DTA_OK) return rc;
     if (dx) return fail(ctx, DTA_ERR_UNSUPPORTED, "gradient of the crops (dx) is not built yet; the reference feeds requires_grad=False inputs");
   }
-  if (rtiles > 0) {
-    StageScope sc(ctx, "bwd.small_param_grads", st);
-    if (rtiles > reduce_tiles_bound(classes, nb)) return fail(ctx, DTA_ERR_UNSUPPORTED, "reduction tile bound exceeded");
-    batched_reduce_kernel<<<dim3(rtiles, kReduceSplits), 256, 0, st>>>(rtab, B, W.rpart);
-    DTA_CHECK_LAUNCH(ctx, "batched_reduce");
-    batched_reduce_finish_kernel<<<rtiles, 256, 0, st>>>(rtab, W.rpart);
-    DTA_CHECK_LAUNCH(ctx, "batched_reduce_finish");
-  }
+  side.join();
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("backward: ") + cudaGetErrorString(e));
   return DTA_OK;

@@ -97,6 +97,39 @@ inline int fail(dta_ctx* ctx, int code, const std::string& msg) {
   return code;
 }
 
+// Fork/join of the library-owned side stream around one C-ABI call (option "overlap").  Inactive (everything on the caller's
+// stream) when the option is 0, when no side stream exists, or while stage profiling is on (stage times stay attributable).
+struct SideStream {
+  dta_ctx* ctx;
+  cudaStream_t main;
+  bool on;
+  bool pending = false;   // side work enqueued since the last join
+  SideStream(dta_ctx* c, cudaStream_t m) : ctx(c), main(m), on(c->overlap != 0 && c->profile == 0 && c->side != nullptr && !c->sync_events.empty()) {}
+  cudaStream_t stream() const { return on ? ctx->side : main; }
+  cudaEvent_t next_event() {
+    cudaEvent_t e = ctx->sync_events[ctx->sync_next];
+    ctx->sync_next = (ctx->sync_next + 1) % ctx->sync_events.size();
+    return e;
+  }
+  // the side stream waits for everything enqueued on the caller's stream so far
+  void wait_main() {
+    if (!on) return;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, main);
+    cudaStreamWaitEvent(ctx->side, e, 0);
+    pending = true;
+  }
+  // the caller's stream waits for everything enqueued on the side stream so far
+  void join() {
+    if (!on || !pending) return;
+    cudaEvent_t e = next_event();
+    cudaEventRecord(e, ctx->side);
+    cudaStreamWaitEvent(main, e, 0);
+    pending = false;
+  }
+  ~SideStream() { join(); }   // error paths: never leave the caller's stream (or a graph capture) with unjoined work
+};
+
 #define DTA_CHECK_LAUNCH(ctx, what)                                                        \
   do {                                                                                     \
     cudaError_t e__ = cudaGetLastError();                                                  \

@@ -222,6 +222,32 @@ def test_graphed_step_equals_eager_step():
         assert torch.equal(pe.grad, pg.grad), k
 
 
+@pytest.mark.parametrize("kind,bands,classes,batch", [("hang2020", 369, 50, 48), ("spectral", 30, 7, 5), ("vanilla", 12, 4, 9)])
+def test_side_stream_overlap_is_bit_identical(kind, bands, classes, batch):
+    """Option "overlap" only moves launches to the library's side stream (fork/join with events): same kernels, same
+    arithmetic order, so scores, loss, gradients and BatchNorm buffers must be bit-identical with it on and off."""
+    from deeptreeattention_b200 import _capi
+    table = orc.init_params(kind, bands, classes, 21, perturb_bn=True)
+    x, y = orc.make_inputs(batch, bands, classes, 21)
+    dev = torch.cuda.current_device()
+    runs = []
+    try:
+        for overlap in (1, 0, 1):
+            _capi.set_option(dev, "overlap", overlap)
+            runs.append(run_cuda(kind, bands, classes, table, x, y, "R2" if kind != "vanilla" else "R1", True))
+    finally:
+        _capi.set_option(dev, "overlap", 1)
+    for other in runs[1:]:
+        assert other[0] == runs[0][0]
+        assert np.array_equal(other[1], runs[0][1])
+        for k, g in runs[0][3].items():
+            assert (g is None) == (other[3][k] is None), k
+            if g is not None:
+                assert torch.equal(g, other[3][k]), k
+        for k, b in runs[0][4].items():
+            assert torch.equal(b, other[4][k]), k
+
+
 def test_year_ensemble_matches_oracle_and_skips_zero_years():
     """learned_ensemble (src/models/year.py:9-33; shapes of tests/test_year.py): mean of the last heads of the
     non-zero years, each year network checked against the oracle."""
