@@ -41,6 +41,8 @@ bool describe(int kind, NetDesc* d) {
     case DTA_NET_SPECTRAL: *d = {1, {BR_SPECTRAL, BR_NONE}, 3}; return true;
     case DTA_NET_SPATIAL: *d = {1, {BR_SPATIAL, BR_NONE}, 3}; return true;
     case DTA_NET_VANILLA: *d = {1, {BR_NONE, BR_NONE}, 1}; return true;
+    case DTA_NET_SPECTRAL_PAIR: *d = {2, {BR_SPECTRAL, BR_SPECTRAL}, 6}; return true;
+    case DTA_NET_SPATIAL_PAIR: *d = {2, {BR_SPATIAL, BR_SPATIAL}, 6}; return true;
     default: return false;
   }
 }
@@ -330,8 +332,9 @@ ConvSrc src_dz(const float* da, const float* z, int cin, int ctot, int hw, const
   return s;
 }
 
-AttnParams attn_params(const dta_tensors* p, const SavedLayout& L, const NetDesc& d, int k, bool vanilla_head) {
+AttnParams attn_params(const dta_tensors* p, const SavedLayout& L, const NetDesc& d, int k, bool vanilla_head, int classes_second = 0) {
   AttnParams a{};
+  a.classes_g[1] = classes_second;
   for (int g = 0; g < 2; ++g) {
     a.btype[g] = d.btype[g];
     if (g >= d.nb) continue;
@@ -499,8 +502,9 @@ int dta_query_sizes(const dta_shape* shape, dta_sizes* out) {
   return DTA_OK;
 }
 
-int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_tensors* params,
-                float* const scores[6], float* joint, void* saved, void* workspace, void* cuda_stream) {
+// Shared body of dta_forward and dta_forward_pair (classes_second > 0: branch 1's heads have that many classes).
+static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second, const float* x, const dta_tensors* params,
+                        float* const scores[6], float* joint, void* saved, void* workspace, void* cuda_stream) {
   NetDesc d;
   int rc = check_shape(ctx, shape, &d);
   if (rc != DTA_OK) return rc;
@@ -623,7 +627,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     auto kern = attn_fwd_kernel<32, 11, false>;
     const size_t sm = attn_fwd_smem<32, 11, false>();
     allow_smem(kern, sm);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], attn_params(params, L, d, 0, false), classes, L.att[0], L.feat[0], score_ptrs(0),
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], attn_params(params, L, d, 0, false, classes_second), classes, L.att[0], L.feat[0], score_ptrs(0),
                                               tcp ? L.a1p : nullptr, tg.rows11, nb * 4);
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<1>");
   }
@@ -654,7 +658,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     auto kern = attn_fwd_kernel<64, 11, true>;
     const size_t sm = attn_fwd_smem<64, 11, true>();
     allow_smem(kern, sm);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], attn_params(params, L, d, 1, false), classes, L.att[1], L.feat[1], score_ptrs(1),
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], attn_params(params, L, d, 1, false, classes_second), classes, L.att[1], L.feat[1], score_ptrs(1),
                                               tcp ? L.a2p : nullptr, tg.rows5, nb * 8);
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<2>");
   }
@@ -684,7 +688,7 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
     auto kern = attn_fwd_kernel<128, 5, true>;
     const size_t sm = attn_fwd_smem<128, 5, true>();
     allow_smem(kern, sm);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], attn_params(params, L, d, 2, vanilla), classes, L.att[2], L.feat[2], score_ptrs(2), nullptr, 0, 0);
+    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], attn_params(params, L, d, 2, vanilla, classes_second), classes, L.att[2], L.feat[2], score_ptrs(2), nullptr, 0, 0);
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<3>");
   }
   // 5. alpha blend + copies of the last-head scores for dalpha
@@ -699,6 +703,23 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("forward: ") + cudaGetErrorString(e));
   return DTA_OK;
+}
+
+int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_tensors* params,
+                float* const scores[6], float* joint, void* saved, void* workspace, void* cuda_stream) {
+  if (ctx && shape && (shape->net_kind == DTA_NET_SPECTRAL_PAIR || shape->net_kind == DTA_NET_SPATIAL_PAIR))
+    return fail(ctx, DTA_ERR_INVALID_ARG, "pair kinds are inference fan-out only: use dta_forward_pair");
+  return forward_impl(ctx, shape, 0, x, params, scores, joint, saved, workspace, cuda_stream);
+}
+
+int dta_forward_pair(dta_ctx* ctx, const dta_shape* shape, int classes_second, const float* x, const dta_tensors* params,
+                     float* const scores[6], void* saved, void* workspace, void* cuda_stream) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  if (!shape || (shape->net_kind != DTA_NET_SPECTRAL_PAIR && shape->net_kind != DTA_NET_SPATIAL_PAIR))
+    return fail(ctx, DTA_ERR_INVALID_ARG, "dta_forward_pair needs net_kind DTA_NET_SPECTRAL_PAIR or DTA_NET_SPATIAL_PAIR");
+  if (shape->training) return fail(ctx, DTA_ERR_UNSUPPORTED, "dta_forward_pair is eval-mode only (prediction fan-out)");
+  if (classes_second <= 0 || classes_second > 4096) return fail(ctx, DTA_ERR_INVALID_ARG, "classes_second must be in [1, 4096]");
+  return forward_impl(ctx, shape, classes_second, x, params, scores, nullptr, saved, workspace, cuda_stream);
 }
 
 int dta_preprocess_crops(dta_ctx* ctx, const int16_t* raw, int batch, int bands_in, int clip, float* out, void* cuda_stream) {
@@ -791,6 +812,8 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   NetDesc d;
   int rc = check_shape(ctx, shape, &d);
   if (rc != DTA_OK) return rc;
+  if (shape->net_kind == DTA_NET_SPECTRAL_PAIR || shape->net_kind == DTA_NET_SPATIAL_PAIR)
+    return fail(ctx, DTA_ERR_UNSUPPORTED, "pair kinds are inference fan-out only: no backward");
   if (!x || !saved || !workspace || !grads || !dscores) return fail(ctx, DTA_ERR_INVALID_ARG, "x, saved, workspace, dscores and grads are required");
   if ((reinterpret_cast<uintptr_t>(saved) | reinterpret_cast<uintptr_t>(workspace)) & 255u)
     return fail(ctx, DTA_ERR_INVALID_ARG, "saved and workspace must be 256-byte aligned (bulk copies and vector stores rely on it)");

@@ -21,6 +21,8 @@ struct AttnParams {
   const float* b0[2]; const float* b1[2];
   const float* pool_w[2]; const float* pool_b[2];
   const float* fc_w[2]; const float* fc_b[2];   // head; nullptr = no head at this block
+  int classes_g[2];                             // forward only: per-branch class count (0 = the launch's common `classes`); the
+                                                // inference fan-out pairs networks of different levels (dta_forward_pair)
 };
 
 template <int C, int SPRE, bool POOL>
@@ -240,8 +242,9 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
   for (int f = tid; f < F; f += kAttnThreads) feat_row[f] = s_feat[f];
   const float* fw = prm.fc_w[g];
   if (fw != nullptr) {
-    float* sc_out = scores.p[g] + (size_t)b * classes;
-    for (int cls = warp; cls < classes; cls += kAttnThreads / 32) {
+    const int ncls = prm.classes_g[g] > 0 ? prm.classes_g[g] : classes;
+    float* sc_out = scores.p[g] + (size_t)b * ncls;
+    for (int cls = warp; cls < ncls; cls += kAttnThreads / 32) {
       float a = 0.f;
       for (int f = lane; f < F; f += 32) a = fmaf(s_feat[f], __ldg(fw + (size_t)cls * F + f), a);
       a = warp_sum(a);

@@ -583,6 +583,77 @@ __global__ void blk_batch_sum_kernel(const float* __restrict__ U, size_t ldu, co
   }
 }
 
+// ---- year ensemble on the device (src/models/year.py:24-33, src/models/multi_stage.py:302,314) ----------------------------
+constexpr int kMaxYears = 16;
+constexpr int kYearSumBlocks = 1024;   // partial sums per year (fixed order)
+struct YearPtrs {
+  const float* p[kMaxYears];
+};
+
+// partial[y][blk] = sum of one grid-stride slice of crops[y]
+__global__ void __launch_bounds__(kBlkThreads) crops_sum_partial_kernel(YearPtrs crops, size_t elems, float* __restrict__ partial) {
+  __shared__ float s_w[kBlkThreads / 32];
+  const float* src = crops.p[blockIdx.y];
+  float s = 0.f;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (elems & 3u) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems / 4; i += stride) {
+      const float4 v = __ldg(s4 + i);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += stride) s += __ldg(src + i);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < kBlkThreads / 32; ++i) t += s_w[i];
+    partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+// one warp per year: flags[y] = (sum != 0)
+__global__ void crops_nonzero_finish_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ flags) {
+  const int y = blockIdx.x, lane = threadIdx.x;
+  float s = 0.f;
+  for (int i = lane; i < nblk; i += 32) s += partial[(size_t)y * nblk + i];
+  s = warp_sum(s);
+  if (lane == 0) flags[y] = (s != 0.f) ? 1.f : 0.f;
+}
+
+// One warp per crop row: mean of the active years' scores, optional row softmax.
+__global__ void __launch_bounds__(kBlkThreads)
+ensemble_mean_kernel(YearPtrs scores, const float* __restrict__ flags, int n, int B, int K, int softmax, float* __restrict__ out) {
+  const int row = blockIdx.x * (kBlkThreads / 32) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int lane = threadIdx.x & 31;
+  float count = 0.f;
+  for (int y = 0; y < n; ++y) count += (flags == nullptr || flags[y] != 0.f) ? 1.f : 0.f;
+  float* o = out + (size_t)row * K;
+  float mx = -INFINITY;
+  for (int k = lane; k < K; k += 32) {
+    float acc = 0.f;
+    for (int y = 0; y < n; ++y)
+      if (flags == nullptr || flags[y] != 0.f) acc += scores.p[y][(size_t)row * K + k];
+    const float v = acc / count;
+    o[k] = v;
+    mx = fmaxf(mx, v);
+  }
+  if (!softmax) return;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float sum = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float e = expf(o[k] - mx);
+    o[k] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  for (int k = lane; k < K; k += 32) o[k] = o[k] / sum;
+}
+
 // ---- fused Adam over a table of parameter tensors (torch.optim.Adam as configured in src/main.py:135-136 and
 // src/models/multi_stage.py:258-262: lr from the config, betas (0.9, 0.999), eps 1e-8, no weight decay, no amsgrad) ------------
 constexpr int kAdamMaxTensors = 96;

@@ -265,6 +265,50 @@ int dta_classifier_backward(dta_ctx* ctx, int batch, int in_features, int classe
   return DTA_OK;
 }
 
+int dta_crops_nonzero(dta_ctx* ctx, int n_years, const float* const crops[], size_t elems, float* flags, void* workspace,
+                      void* cuda_stream) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  if (n_years <= 0 || n_years > kMaxYears) return fail(ctx, DTA_ERR_INVALID_ARG, "need 1 <= n_years <= 16");
+  if (!crops || !flags || !workspace || elems == 0) return fail(ctx, DTA_ERR_INVALID_ARG, "crops, flags, workspace and elems are required");
+  YearPtrs yp{};
+  for (int y = 0; y < n_years; ++y) {
+    if (!crops[y]) return fail(ctx, DTA_ERR_INVALID_ARG, "crops[y] is NULL");
+    yp.p[y] = crops[y];
+  }
+  int rc = begin_call(ctx);
+  if (rc != DTA_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  StageScope sc(ctx, "year.crops_nonzero", st);
+  size_t want = (elems / 4 + kBlkThreads - 1) / kBlkThreads;
+  int nblk = (int)(want < 1 ? 1 : (want > (size_t)kYearSumBlocks ? (size_t)kYearSumBlocks : want));
+  float* partial = static_cast<float*>(workspace);
+  crops_sum_partial_kernel<<<dim3(nblk, n_years), kBlkThreads, 0, st>>>(yp, elems, partial);
+  DTA_CHECK_LAUNCH(ctx, "crops_sum_partial");
+  crops_nonzero_finish_kernel<<<n_years, 32, 0, st>>>(partial, nblk, flags);
+  DTA_CHECK_LAUNCH(ctx, "crops_nonzero_finish");
+  return DTA_OK;
+}
+
+int dta_ensemble_mean(dta_ctx* ctx, int n_years, const float* const scores[], const float* flags, int batch, int classes,
+                      int softmax, float* out, void* cuda_stream) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  if (n_years <= 0 || n_years > kMaxYears) return fail(ctx, DTA_ERR_INVALID_ARG, "need 1 <= n_years <= 16");
+  if (!scores || !out || batch <= 0 || classes <= 0) return fail(ctx, DTA_ERR_INVALID_ARG, "scores, out, batch and classes are required");
+  YearPtrs yp{};
+  for (int y = 0; y < n_years; ++y) {
+    if (!scores[y]) return fail(ctx, DTA_ERR_INVALID_ARG, "scores[y] is NULL");
+    yp.p[y] = scores[y];
+  }
+  int rc = begin_call(ctx);
+  if (rc != DTA_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  StageScope sc(ctx, "year.ensemble_mean", st);
+  const int rows_per_block = kBlkThreads / 32;
+  ensemble_mean_kernel<<<(batch + rows_per_block - 1) / rows_per_block, kBlkThreads, 0, st>>>(yp, flags, n_years, batch, classes, softmax, out);
+  DTA_CHECK_LAUNCH(ctx, "ensemble_mean");
+  return DTA_OK;
+}
+
 int dta_adam_step(dta_ctx* ctx, int n_tensors, float* const params[], const float* const grads[], const int64_t numel[],
                   const int64_t offset[], float* exp_avg, float* exp_avg_sq, double* param64, const double* grad64,
                   double* moments64, const dta_adam_hyper* h, int64_t* step_device, const float* lr_device, void* cuda_stream) {

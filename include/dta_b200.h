@@ -44,7 +44,10 @@ typedef enum dta_net_kind {
   DTA_NET_HANG2020 = 0, /* Hang2020.Hang2020          (Hang2020.py:242-263): 2 branches + alpha */
   DTA_NET_SPECTRAL = 1, /* Hang2020.spectral_network  (:206-240)                               */
   DTA_NET_SPATIAL = 2,  /* Hang2020.spatial_network   (:170-204)                               */
-  DTA_NET_VANILLA = 3   /* Hang2020.vanilla_CNN       (:33-53)                                 */
+  DTA_NET_VANILLA = 3,  /* Hang2020.vanilla_CNN       (:33-53)                                 */
+  /* inference fan-out (dta_forward_pair, dta_query_sizes): TWO networks of one kind on the same crops */
+  DTA_NET_SPECTRAL_PAIR = 4,
+  DTA_NET_SPATIAL_PAIR = 5
 } dta_net_kind;
 
 typedef struct dta_shape {
@@ -158,6 +161,20 @@ int dta_forward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_
                 void* cuda_stream);
 
 /*
+ * Prediction fan-out.  MultiStage.predict_step (src/models/multi_stage.py:306-318) runs every level's model on the SAME
+ * crops; per year that is one spectral_network per level on one crop tensor.  This call evaluates TWO such networks in one
+ * pass: the crops are read once and block 1's convolution runs with both networks' filters side by side (N = 64, exactly
+ * the Hang2020 two-branch shape of dta_forward).  Eval mode only (running statistics; nothing is updated).
+ *   shape      : net_kind DTA_NET_SPECTRAL_PAIR / DTA_NET_SPATIAL_PAIR, training = 0, classes = class count of network 0
+ *   classes_second : class count of network 1 (levels have different label sets)
+ *   params     : branch[0] = network 0, branch[1] = network 1 (alpha ignored)
+ *   scores     : [0..2] = heads of network 0 (batch, classes), [3..5] = heads of network 1 (batch, classes_second)
+ *   saved / workspace : dta_query_sizes(shape) with the pair kind and classes = max of the two
+ */
+int dta_forward_pair(dta_ctx* ctx, const dta_shape* shape, int classes_second, const float* x, const dta_tensors* params,
+                     float* const scores[6], void* saved, void* workspace, void* cuda_stream);
+
+/*
  * Backward of the forward above (what autograd derives in the reference).
  *   dscores[i]: upstream gradient per head, (batch, classes) float32, NULL = head unused
  *   djoint    : upstream gradient of `joint`, NULL = unused
@@ -215,6 +232,20 @@ int dta_grad_allreduce_sizes(size_t n_float4, size_t n_double, int world, size_t
                              size_t* scratch_bytes);
 int dta_grad_allreduce(dta_ctx* ctx, int rank, int world, void* const peer_buffers[], const void* multicast_buffer,
                        size_t n_float4, size_t n_double, void* scratch, void* sync_words, void* cuda_stream);
+
+/*
+ * Year ensemble on the device.  learned_ensemble.forward (src/models/year.py:24-33) skips a year whose crop tensor sums to
+ * zero (`if x.sum() == 0: continue`, a device->host sync per year) and averages the last-head scores of the others.
+ *   dta_crops_nonzero : flags[y] = (sum of crops[y] != 0) ? 1 : 0 for n_years <= 16 tensors of `elems` floats each
+ *                       (workspace: n_years * 4096 bytes) -- the same test, without leaving the device
+ *   dta_ensemble_mean : out[b][k] = mean over the years with flags[y] != 0 (flags NULL: all) of scores[y][b][k], followed by
+ *                       F.softmax(dim=1) when softmax != 0 (MultiStage.validation_step / predict_step,
+ *                       multi_stage.py:302,314).  No active year gives NaN rows (the reference raises on the empty stack).
+ */
+int dta_crops_nonzero(dta_ctx* ctx, int n_years, const float* const crops[], size_t elems, float* flags, void* workspace,
+                      void* cuda_stream);
+int dta_ensemble_mean(dta_ctx* ctx, int n_years, const float* const scores[], const float* flags, int batch, int classes,
+                      int softmax, float* out, void* cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Stand-alone building blocks.  The reference's tests and notebooks call conv_module, spatial_attention,
