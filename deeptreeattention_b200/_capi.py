@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 DTA_OK = 0
-NET_HANG2020, NET_SPECTRAL, NET_SPATIAL, NET_VANILLA = 0, 1, 2, 3
+NET_HANG2020, NET_SPECTRAL, NET_SPATIAL, NET_VANILLA, NET_SPECTRAL_PAIR, NET_SPATIAL_PAIR = 0, 1, 2, 3, 4, 5
 
 
 class Shape(C.Structure):
@@ -70,7 +70,8 @@ EXPORTS = ["dta_abi_version", "dta_create", "dta_destroy", "dta_last_error", "dt
            "dta_cross_entropy_heads", "dta_preprocess_crops", "dta_grad_allreduce_sizes", "dta_grad_allreduce",
            "dta_plane_mean", "dta_plane_mean_backward", "dta_conv_module_workspace_bytes", "dta_conv_module_forward",
            "dta_conv_module_backward", "dta_attention_sizes", "dta_attention_forward", "dta_attention_backward",
-           "dta_classifier_forward", "dta_classifier_backward", "dta_adam_step"]
+           "dta_classifier_forward", "dta_classifier_backward", "dta_adam_step", "dta_forward_pair", "dta_crops_nonzero",
+           "dta_ensemble_mean"]
 
 
 def sources():
@@ -172,6 +173,9 @@ def lib():
         L.dta_classifier_forward.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp]
         L.dta_classifier_backward.argtypes = [vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp]
         L.dta_adam_step.argtypes = [vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(AdamHyper), vp, vp, vp]
+        L.dta_forward_pair.argtypes = [vp, C.POINTER(Shape), ci, vp, C.POINTER(Tensors), C.POINTER(C.c_void_p * 6), vp, vp, vp]
+        L.dta_crops_nonzero.argtypes = [vp, ci, C.POINTER(C.c_void_p * 16), sz, vp, vp, vp]
+        L.dta_ensemble_mean.argtypes = [vp, ci, C.POINTER(C.c_void_p * 16), vp, ci, ci, ci, vp, vp]
         for name in EXPORTS[15:]:
             getattr(L, name).restype = C.c_int
         _lib = L

@@ -609,7 +609,7 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
   auto bn_finalize = [&](int k, int nblk_k) -> int {
     StageScope sc(ctx, "fwd.bn_finalize", st);
     const int ctot = nb * kC[k];
-    bn_fwd_finalize_kernel<<<(ctot + 31) / 32, 32 * kBnSlices, 0, st>>>(W.stats, nblk_k, ctot, (double)B * kHWpre[k], bn_params(params, d, k),
+    bn_fwd_finalize_kernel<<<(ctot + kBnCh - 1) / kBnCh, kBnCh * kBnSlices, 0, st>>>(W.stats, nblk_k, ctot, (double)B * kHWpre[k], bn_params(params, d, k),
                                                                     shape->training, L.bn_mean[k], L.bn_istd[k], L.bn_scale[k], L.bn_shift[k]);
     DTA_CHECK_LAUNCH(ctx, "bn_fwd_finalize");
     return DTA_OK;
@@ -908,7 +908,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   auto bn_bwd = [&](int k) -> int {
     StageScope sc(ctx, "bwd.bn_finalize", st);
     const int ctot = nb * kC[k];
-    bn_bwd_finalize_kernel<<<(ctot + 31) / 32, 32 * kBnSlices, 0, st>>>(W.bnrows, B, nb, kC[k], (double)B * kHWpre[k], bn_params(params, d, k),
+    bn_bwd_finalize_kernel<<<(ctot + kBnCh - 1) / kBnCh, kBnCh * kBnSlices, 0, st>>>(W.bnrows, B, nb, kC[k], (double)B * kHWpre[k], bn_params(params, d, k),
                                                                     L.bn_mean[k], L.bn_istd[k], shape->training, bn_grads(k), W.k0[k], W.k1[k], W.k2[k]);
     DTA_CHECK_LAUNCH(ctx, "bn_bwd_finalize");
     return DTA_OK;

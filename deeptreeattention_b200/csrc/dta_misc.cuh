@@ -65,18 +65,34 @@ struct BnParams {
   int c_per_branch;
 };
 
-constexpr int kBnSlices = 32;   // row slices per block in the BatchNorm finalize kernels (block = 32 channels x 32 slices)
+constexpr int kBnCh = 8;         // channels per block in the BatchNorm finalize kernels
+constexpr int kBnSlices = 128;   // row slices per block (block = 8 channels x 128 slices = 1024 threads)
 
-// Block = 32 channels x 32 row slices (coalesced 128-byte reads), fp64 accumulation in fixed order.
+// Sum over the kBnSlices row slices of a block for every channel (fixed order): xor-shuffles over the 4 slices a warp holds,
+// then the 32 per-warp partials through shared memory.  Valid in the threads with ry == 0.
+__device__ __forceinline__ void bn_block_sum2(double& a, double& b, double (*sa)[kBnCh], double (*sb)[kBnCh]) {
+  a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
+  a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < kBnCh) { sa[warp][lane] = a; sb[warp][lane] = b; }
+  __syncthreads();
+  if (threadIdx.x < kBnCh) {
+    a = 0.0; b = 0.0;
+#pragma unroll 8
+    for (int w = 0; w < kBnSlices * kBnCh / 32; ++w) { a += sa[w][threadIdx.x]; b += sb[w][threadIdx.x]; }
+  }
+}
+
+// Block = 8 channels x 128 row slices, fp64 accumulation in fixed order (few rows per thread: the kernel is pure latency).
 // training: reduce the conv kernels' partial sums, produce mean / invstd / scale / shift and update the running
 // statistics (momentum 0.1, unbiased variance) exactly like nn.BatchNorm2d in train(); eval: use running statistics.
-__global__ void __launch_bounds__(32 * kBnSlices)
+__global__ void __launch_bounds__(kBnCh * kBnSlices)
 bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int nblk, int ctot, double count, BnParams bn,
                        int training, float* __restrict__ mean, float* __restrict__ istd, float* __restrict__ scale,
                        float* __restrict__ shift) {
-  __shared__ double ss[kBnSlices][33], sq[kBnSlices][33];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int ch = blockIdx.x * 32 + cx;
+  __shared__ double ss[kBnSlices * kBnCh / 32][kBnCh], sq[kBnSlices * kBnCh / 32][kBnCh];
+  const int cx = threadIdx.x & (kBnCh - 1), ry = threadIdx.x / kBnCh;
+  const int ch = blockIdx.x * kBnCh + cx;
   double s = 0.0, q = 0.0;
   if (training && ch < ctot) {
 #pragma unroll 4
@@ -86,13 +102,8 @@ bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int n
       q += (double)v.y;
     }
   }
-  ss[ry][cx] = s;
-  sq[ry][cx] = q;
-  __syncthreads();
+  bn_block_sum2(s, q, ss, sq);
   if (ry != 0 || ch >= ctot) return;
-  s = 0.0; q = 0.0;
-#pragma unroll
-  for (int k = 0; k < kBnSlices; ++k) { s += ss[k][cx]; q += sq[k][cx]; }
   const int br = ch / bn.c_per_branch, c = ch - br * bn.c_per_branch;
   float m, is;
   if (training) {
@@ -122,18 +133,18 @@ struct BnGrads {
   float* dconv_b[2];
 };
 
-// Block = 32 channels x 32 crop slices.  rows[b][g][2C] hold per-crop (sum da | sum da*zhat); reduce over the batch in
+// Block = 8 channels x 128 crop slices.  rows[b][g][2C] hold per-crop (sum da | sum da*zhat); reduce over the batch in
 // fp64 (fixed order), emit dgamma / dbeta / dbias and the coefficients of
 //   dz = k0*da + k1*z + k2     (train: k0 = gamma*istd, k1 = -k0*istd*dgamma/N,
 //                               k2 = -k0*dbeta/N - k1*mean;  eval: k1 = k2 = 0)
-__global__ void __launch_bounds__(32 * kBnSlices)
+__global__ void __launch_bounds__(kBnCh * kBnSlices)
 bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, int G, int C, double count, BnParams bn, const float* __restrict__ mean,
                        const float* __restrict__ istd, int training, BnGrads gr, float* __restrict__ k0, float* __restrict__ k1,
                        float* __restrict__ k2) {
-  __shared__ double sa[kBnSlices][33], sb[kBnSlices][33];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  __shared__ double sa[kBnSlices * kBnCh / 32][kBnCh], sb[kBnSlices * kBnCh / 32][kBnCh];
+  const int cx = threadIdx.x & (kBnCh - 1), ry = threadIdx.x / kBnCh;
   const int ctot = G * C;
-  const int ch = blockIdx.x * 32 + cx;
+  const int ch = blockIdx.x * kBnCh + cx;
   const int g = ch / C, c = ch - g * C;
   double s1 = 0.0, s2 = 0.0;
   if (ch < ctot) {
@@ -144,13 +155,8 @@ bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, int G, int C, doub
       s2 += (double)__ldg(r + C + c);
     }
   }
-  sa[ry][cx] = s1;
-  sb[ry][cx] = s2;
-  __syncthreads();
+  bn_block_sum2(s1, s2, sa, sb);
   if (ry != 0 || ch >= ctot) return;
-  s1 = 0.0; s2 = 0.0;
-#pragma unroll
-  for (int k = 0; k < kBnSlices; ++k) { s1 += sa[k][cx]; s2 += sb[k][cx]; }
   const int br = ch / bn.c_per_branch, cb = ch - br * bn.c_per_branch;
   const double gam = bn.gamma[br][cb];
   const double is = istd[ch], mu = mean[ch];

@@ -146,10 +146,18 @@ class FusedAdam(torch.optim.Optimizer):
                     n = len(chunk)
                     hyper = _capi.AdamHyper(float(group["lr"]), float(beta1), float(beta2), float(group["eps"]),
                                             float(group["weight_decay"]), max(int(step_no), 1))
-                    pp = (C.c_void_p * max(n, 1))(*[p.data_ptr() for p in chunk])
-                    gp = (C.c_void_p * max(n, 1))(*[p.grad.data_ptr() for p in chunk])
-                    ne = (C.c_int64 * max(n, 1))(*[p.numel() for p in chunk])
-                    of = (C.c_int64 * max(n, 1))(*[st["offsets"][p] for p in chunk])
+                    # the pointer tables only change when a tensor moves (the fused backward keeps every gradient a view of one
+                    # persistent flat buffer): build them once per layout
+                    key = tuple(p.data_ptr() for p in chunk) + tuple(p.grad.data_ptr() for p in chunk)
+                    cached = st.setdefault("tables", {}).get(key)
+                    if cached is None:
+                        if len(st["tables"]) > 8:
+                            st["tables"].clear()
+                        cached = ((C.c_void_p * max(n, 1))(*key[:n]), (C.c_void_p * max(n, 1))(*key[n:]),
+                                  (C.c_int64 * max(n, 1))(*[p.numel() for p in chunk]),
+                                  (C.c_int64 * max(n, 1))(*[st["offsets"][p] for p in chunk]))
+                        st["tables"][key] = cached
+                    pp, gp, ne, of = cached
                     last = ci == len(chunks) - 1
                     use64 = p64 is not None and last
                     # the device step counter ticks once per step: on the first launch of the group

@@ -1,12 +1,76 @@
 """Drop-in for the reference's ``src/models/year.py``: one spectral network per year, all-zero years skipped,
-mean of the last-head scores (reference :9-33).  Every year network runs through the CUDA library."""
+mean of the last-head scores (reference :9-33).  Every year network runs through the CUDA library.
+
+Training keeps the reference's control flow (a skipped year must not touch its BatchNorm statistics, so the zero test
+has to reach the host -- ONE sync for all years instead of the reference's one per year).  Inference
+(``eval()`` under ``torch.no_grad()``: validation / predict) never leaves the device: ``dta_crops_nonzero`` computes the
+per-year flags, every year network runs, and ``dta_ensemble_mean`` averages the flagged years (optionally fused with the
+softmax of ``MultiStage.predict_step``), so the whole ensemble is stream-ordered and graph-capturable."""
 from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
 
 import torch
 from torch import nn
 from torch.nn import Module
 
-from . import Hang2020
+from . import Hang2020, _capi
+
+
+def _handle(dev):
+    return _capi.context(dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+def _check_years(images: Sequence[torch.Tensor]):
+    if len(images) == 0 or len(images) > 16:
+        raise ValueError("expected between 1 and 16 per-year crop tensors")
+    for x in images:
+        if not isinstance(x, torch.Tensor) or not x.is_cuda:
+            raise RuntimeError("deeptreeattention_b200 has no CPU path: every year's crops must live on a CUDA (sm_100) device")
+        if x.dtype != torch.float32 or x.shape != images[0].shape or x.device != images[0].device:
+            raise ValueError("every year's crops must be float32 tensors of one shape on one device")
+
+
+def crops_nonzero(images: Sequence[torch.Tensor]) -> torch.Tensor:
+    """float32 (years,) device tensor: 1 where ``images[y].sum() != 0`` (the reference's skip test, year.py:27), else 0."""
+    _check_years(images)
+    imgs = [x.contiguous() for x in images]
+    dev = imgs[0].device
+    handle = _handle(dev)
+    with torch.cuda.device(dev):
+        flags = torch.empty(len(imgs), dtype=torch.float32, device=dev)
+        work = torch.empty(len(imgs) * 4096, dtype=torch.uint8, device=dev)
+        ptrs = (C.c_void_p * 16)(*[x.data_ptr() for x in imgs] + [None] * (16 - len(imgs)))
+        rc = _capi.lib().dta_crops_nonzero(handle, len(imgs), C.byref(ptrs), imgs[0].numel(), flags.data_ptr(), work.data_ptr(),
+                                           torch.cuda.current_stream(dev).cuda_stream)
+    _capi.check(handle, rc, "dta_crops_nonzero")
+    return flags
+
+
+def ensemble_mean(scores: Sequence[torch.Tensor], flags: Optional[torch.Tensor], softmax: bool = False) -> torch.Tensor:
+    """Mean over the flagged years of (batch, classes) score tensors, optionally followed by ``F.softmax(dim=1)``
+    (``torch.stack(year_scores, axis=1).mean(axis=1)``, year.py:33; softmax: multi_stage.py:302,314).  No autograd."""
+    scores = [s.detach().contiguous() for s in scores]
+    if not scores or len(scores) > 16:
+        raise ValueError("expected between 1 and 16 score tensors")
+    dev = scores[0].device
+    if dev.type != "cuda":
+        raise RuntimeError("deeptreeattention_b200 has no CPU path: scores must live on a CUDA (sm_100) device")
+    B, K = scores[0].shape
+    for s in scores:
+        if s.dtype != torch.float32 or s.shape != (B, K) or s.device != dev:
+            raise ValueError("every year's scores must be float32 (batch, classes) on one device")
+    if flags is not None and (flags.dtype != torch.float32 or flags.numel() != len(scores) or flags.device != dev):
+        raise ValueError("flags must be float32 of shape (years,) on the scores' device")
+    handle = _handle(dev)
+    with torch.cuda.device(dev):
+        out = torch.empty((B, K), dtype=torch.float32, device=dev)
+        ptrs = (C.c_void_p * 16)(*[s.data_ptr() for s in scores] + [None] * (16 - len(scores)))
+        rc = _capi.lib().dta_ensemble_mean(handle, len(scores), C.byref(ptrs), flags.data_ptr() if flags is not None else None, B, K,
+                                           int(softmax), out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    _capi.check(handle, rc, "dta_ensemble_mean")
+    return out
 
 
 class learned_ensemble(Module):
@@ -25,11 +89,16 @@ class learned_ensemble(Module):
             self.year_models.append(base_model)
 
     def forward(self, images):
-        """``images``: one (B, bands, 11, 11) tensor per year.  A year whose tensor sums to zero is skipped
-        (reference :27; the test is a device->host sync there too)."""
-        # one host sync for all years instead of one per year
+        """``images``: one (B, bands, 11, 11) tensor per year.  A year whose tensor sums to zero is skipped (reference :27)."""
+        _check_years(images)
+        if not self.training and not torch.is_grad_enabled():
+            # inference: flags, networks and the masked mean all stay on the device (no host sync)
+            flags = crops_nonzero(images)
+            year_scores = [self.year_models[index](x)[-1] for index, x in enumerate(images)]
+            return ensemble_mean(year_scores, flags)
+        # training / autograd: a skipped year must not run at all -- one host sync for all years instead of one per year
         sums = torch.stack([x.sum() for x in images]).tolist()
-        year_scores = []
+        year_scores: List[torch.Tensor] = []
         for index, x in enumerate(images):
             if sums[index] == 0:
                 continue
