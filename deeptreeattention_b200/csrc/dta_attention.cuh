@@ -39,35 +39,86 @@ struct AttnCfg {
 };
 
 // Build r = [maxpool2x2](relu(z*scale+shift)) in shared memory (and optionally the argmax
-// slot of every pooled cell, first-max rule of ATen max_pool2d).
+// slot of every pooled cell, first-max rule of ATen max_pool2d, with the conv output at that slot).
 template <int C, int SPRE, bool POOL>
 __device__ __forceinline__ void build_r(const float* __restrict__ zsrc, const float* __restrict__ scale,
-                                        const float* __restrict__ shift, float* s_r, unsigned char* s_arg) {
+                                        const float* __restrict__ shift, float* s_r, unsigned char* s_arg, float* s_zarg) {
   // POOL: the 2x2 windows are read straight from global memory (each conv output element is needed once, so staging
-  // the pre-pool plane would only cost shared memory and occupancy).  !POOL: s_r already holds the crop's conv
-  // output, bulk-copied by the caller (attn_stage_in), and is rectified in place.
+  // the pre-pool plane would only cost shared memory and occupancy).  All loads of a thread are issued before the first
+  // use: the loop is bound by global-load latency, not by arithmetic.
+  // !POOL: s_r already holds the crop's conv output, bulk-copied by the caller (attn_stage_in), and is rectified in place.
   using Cfg = AttnCfg<C, SPRE, POOL>;
   const int tid = threadIdx.x;
   if (POOL) {
-    for (int i = tid; i < C * Cfg::HW; i += kAttnThreads) {
-      const int c = i / Cfg::HW, p = i - c * Cfg::HW;
-      const int y = p / Cfg::S, x = p - y * Cfg::S;
-      const float sc = __ldg(scale + c), sh = __ldg(shift + c);
-      float best = -INFINITY;
-      int arg = 0;
+    constexpr int N = C * Cfg::HW;
+    constexpr int NIT = (N + kAttnThreads - 1) / kAttnThreads;
+    float zv[NIT][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float a = fmaxf(fmaf(__ldg(zsrc + c * Cfg::HWPRE + (2 * y + (k >> 1)) * SPRE + 2 * x + (k & 1)), sc, sh), 0.f);
-        if (a > best) { best = a; arg = k; }
+    for (int it = 0; it < NIT; ++it) {
+      const int i = tid + it * kAttnThreads;
+      if (i < N) {
+        const int c = i / Cfg::HW, p = i - c * Cfg::HW;
+        const int y = p / Cfg::S, x = p - y * Cfg::S;
+        const float* q = zsrc + c * Cfg::HWPRE + (2 * y) * SPRE + 2 * x;
+        zv[it][0] = __ldg(q); zv[it][1] = __ldg(q + 1); zv[it][2] = __ldg(q + SPRE); zv[it][3] = __ldg(q + SPRE + 1);
       }
-      s_r[i] = best;
-      if (s_arg != nullptr) s_arg[i] = (unsigned char)arg;
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int i = tid + it * kAttnThreads;
+      if (i < N) {
+        const int c = i / Cfg::HW;
+        const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+        float best = -INFINITY, zbest = 0.f;
+        int arg = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = fmaxf(fmaf(zv[it][k], sc, sh), 0.f);
+          if (a > best) { best = a; arg = k; zbest = zv[it][k]; }
+        }
+        s_r[i] = best;
+        if (s_arg != nullptr) { s_arg[i] = (unsigned char)arg; s_zarg[i] = zbest; }
+      }
     }
   } else {
-    for (int i = tid; i < C * Cfg::HW; i += kAttnThreads) {
-      const int c = i / Cfg::HW;
-      s_r[i] = fmaxf(fmaf(s_r[i], __ldg(scale + c), __ldg(shift + c)), 0.f);
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int c = warp; c < C; c += kAttnThreads / 32) {
+      const float sc = __ldg(scale + c), sh = __ldg(shift + c);
+      for (int p = lane; p < Cfg::HW; p += 32) s_r[c * Cfg::HW + p] = fmaxf(fmaf(s_r[c * Cfg::HW + p], sc, sh), 0.f);
     }
+  }
+  __syncthreads();
+}
+
+// out[i] = sum_{j < nin} w[j * nout + i] * s_vec[j] for i < nout, with ALL threads of the CTA: when nout < kAttnThreads
+// (nout a power of two) the j range is split over kAttnThreads / nout thread groups whose partials are added in fixed
+// order through s_part (kAttnThreads floats); loads are unrolled so several are in flight per thread (these loops are
+// bound by L2 latency).  s_out may alias nothing read here.  Ends with a barrier: s_out is ready for every thread.
+__device__ __forceinline__ void fc_cols(const float* __restrict__ w, int nout, int nin, const float* s_vec, float* s_out, float* s_part) {
+  const int tid = threadIdx.x;
+  if (nout >= kAttnThreads) {
+    for (int i = tid; i < nout; i += kAttnThreads) {
+      float a = 0.f;
+#pragma unroll 8
+      for (int j = 0; j < nin; ++j) a = fmaf(__ldg(w + (size_t)j * nout + i), s_vec[j], a);
+      s_out[i] = a;
+    }
+    __syncthreads();
+    return;
+  }
+  const int T = kAttnThreads / nout;
+  const int per = (nin + T - 1) / T;
+  const int i = tid & (nout - 1), q = tid / nout;
+  const int j0 = q * per, j1 = min(nin, j0 + per);
+  float a = 0.f;
+#pragma unroll 8
+  for (int j = j0; j < j1; ++j) a = fmaf(__ldg(w + (size_t)j * nout + i), s_vec[j], a);
+  s_part[tid] = a;
+  __syncthreads();
+  if (tid < nout) {
+    float r = 0.f;
+    for (int k = 0; k < T; ++k) r += s_part[k * nout + tid];
+    s_out[tid] = r;
   }
   __syncthreads();
 }
@@ -121,6 +172,7 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
   float* s_r = smem;                       // C*HW rectified (pooled) activations; !POOL: receives z first
   float* s_v = s_r + C * HW;               // 3*ROW vectors
   float* s_feat = s_v + 3 * Cfg::ROW;      // FEAT_LD
+  float* s_part = s_feat + Cfg::FEAT_LD;   // kAttnThreads partials of the split matrix-vector products
 
   const int b = blockIdx.x, g = blockIdx.y, G = gridDim.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -129,40 +181,51 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
 
   const float* zg = z + ((size_t)b * G + g) * C * Cfg::HWPRE;
   if (!POOL) attn_stage_in(&stage_bar, s_r, zg, C * Cfg::HWPRE, nullptr, nullptr, 0);
-  build_r<C, SPRE, POOL>(zg, scale + g * C, shift + g * C, s_r, nullptr);
+  build_r<C, SPRE, POOL>(zg, scale + g * C, shift + g * C, s_r, nullptr, nullptr);
 
   float* att_row = att + ((size_t)b * G + g) * Cfg::ATT_LD;
   float* feat_row = feat + ((size_t)b * G + g) * Cfg::FEAT_LD;
   int F = 0;
   if (btype == BR_SPECTRAL) {
     float* s_g = s_v; float* s_h = s_v + Cfg::ROW; float* s_s = s_v + 2 * Cfg::ROW;
-    for (int c = warp; c < C; c += kAttnThreads / 32) {
-      float a = 0.f;
-      for (int p = lane; p < HW; p += 32) a += s_r[c * HW + p];
-      a = warp_sum(a);
-      if (lane == 0) s_g[c] = a / (float)HW;
+    if (HW <= 32) {   // few positions per plane: one thread per channel walks them (a warp per channel would idle most lanes)
+      for (int c = tid; c < C; c += kAttnThreads) {
+        float a = 0.f;
+#pragma unroll
+        for (int p = 0; p < HW; ++p) a += s_r[c * HW + p];
+        s_g[c] = a / (float)HW;
+      }
+    } else {
+      for (int c = warp; c < C; c += kAttnThreads / 32) {
+        float a = 0.f;
+        for (int p = lane; p < HW; p += 32) a += s_r[c * HW + p];
+        a = warp_sum(a);
+        if (lane == 0) s_g[c] = a / (float)HW;
+      }
     }
     __syncthreads();
-    for (int i = tid; i < C; i += kAttnThreads) {
-      float a = __ldg(prm.b0[g] + i);
-      const float* w = prm.w0t[g];
-      for (int j = 0; j < C; ++j) a = fmaf(__ldg(w + j * C + i), s_g[j], a);
-      s_h[i] = fmaxf(a, 0.f);
-    }
+    fc_cols(prm.w0t[g], C, C, s_g, s_h, s_part);
+    if (tid < C) s_h[tid] = fmaxf(s_h[tid] + __ldg(prm.b0[g] + tid), 0.f);
     __syncthreads();
-    for (int i = tid; i < C; i += kAttnThreads) {
-      float a = __ldg(prm.b1[g] + i);
-      const float* w = prm.w1t[g];
-      for (int j = 0; j < C; ++j) a = fmaf(__ldg(w + j * C + i), s_h[j], a);
-      s_s[i] = sigmoidf_acc(a);
-    }
+    fc_cols(prm.w1t[g], C, C, s_h, s_s, s_part);
+    if (tid < C) s_s[tid] = sigmoidf_acc(s_s[tid] + __ldg(prm.b1[g] + tid));
     __syncthreads();
-    for (int c = warp; c < C; c += kAttnThreads / 32) {
-      const float sv = s_s[c];
-      float a = 0.f;
-      for (int p = lane; p < HW; p += 32) a += s_r[c * HW + p] * sv;
-      a = warp_sum(a);
-      if (lane == 0) s_feat[c] = a / (float)HW;
+    if (HW <= 32) {
+      for (int c = tid; c < C; c += kAttnThreads) {
+        const float sv = s_s[c];
+        float a = 0.f;
+#pragma unroll
+        for (int p = 0; p < HW; ++p) a += s_r[c * HW + p] * sv;
+        s_feat[c] = a / (float)HW;
+      }
+    } else {
+      for (int c = warp; c < C; c += kAttnThreads / 32) {
+        const float sv = s_s[c];
+        float a = 0.f;
+        for (int p = lane; p < HW; p += 32) a += s_r[c * HW + p] * sv;
+        a = warp_sum(a);
+        if (lane == 0) s_feat[c] = a / (float)HW;
+      }
     }
     F = C;
     for (int i = tid; i < C; i += kAttnThreads) {
@@ -174,6 +237,7 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
     for (int p = tid; p < HW; p += kAttnThreads) {
       float a = __ldg(prm.pool_b[g]);
       const float* w = prm.pool_w[g];
+#pragma unroll 8
       for (int c = 0; c < C; ++c) a = fmaf(__ldg(w + c), s_r[c * HW + p], a);
       s_q[p] = fmaxf(a, 0.f);
     }
@@ -242,13 +306,36 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
   for (int f = tid; f < F; f += kAttnThreads) feat_row[f] = s_feat[f];
   const float* fw = prm.fc_w[g];
   if (fw != nullptr) {
+    // classifier head (Hang2020.py:64): a warp per class, FOUR classes in flight per warp so that the loads and the
+    // shuffle reductions of independent classes overlap
     const int ncls = prm.classes_g[g] > 0 ? prm.classes_g[g] : classes;
     float* sc_out = scores.p[g] + (size_t)b * ncls;
-    for (int cls = warp; cls < ncls; cls += kAttnThreads / 32) {
-      float a = 0.f;
-      for (int f = lane; f < F; f += 32) a = fmaf(s_feat[f], __ldg(fw + (size_t)cls * F + f), a);
-      a = warp_sum(a);
-      if (lane == 0) sc_out[cls] = a + __ldg(prm.fc_b[g] + cls);
+    constexpr int NW = kAttnThreads / 32;
+    for (int cls0 = warp; cls0 < ncls; cls0 += 4 * NW) {
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* w0 = fw + (size_t)cls0 * F;
+      const bool v1 = cls0 + NW < ncls, v2 = cls0 + 2 * NW < ncls, v3 = cls0 + 3 * NW < ncls;
+      const float* w1 = v1 ? w0 + (size_t)NW * F : w0;
+      const float* w2 = v2 ? w0 + (size_t)2 * NW * F : w0;
+      const float* w3 = v3 ? w0 + (size_t)3 * NW * F : w0;
+      for (int f = lane; f < F; f += 32) {
+        const float x = s_feat[f];
+        a[0] = fmaf(x, __ldg(w0 + f), a[0]);
+        a[1] = fmaf(x, __ldg(w1 + f), a[1]);
+        a[2] = fmaf(x, __ldg(w2 + f), a[2]);
+        a[3] = fmaf(x, __ldg(w3 + f), a[3]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+      }
+      if (lane == 0) {
+        sc_out[cls0] = a[0] + __ldg(prm.fc_b[g] + cls0);
+        if (v1) sc_out[cls0 + NW] = a[1] + __ldg(prm.fc_b[g] + cls0 + NW);
+        if (v2) sc_out[cls0 + 2 * NW] = a[2] + __ldg(prm.fc_b[g] + cls0 + 2 * NW);
+        if (v3) sc_out[cls0 + 3 * NW] = a[3] + __ldg(prm.fc_b[g] + cls0 + 3 * NW);
+      }
     }
   }
 }
@@ -256,7 +343,7 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
 template <int C, int SPRE, bool POOL>
 constexpr size_t attn_fwd_smem() {
   using Cfg = AttnCfg<C, SPRE, POOL>;
-  return sizeof(float) * (C * Cfg::HW + 3 * Cfg::ROW + Cfg::FEAT_LD);
+  return sizeof(float) * (C * Cfg::HW + 3 * Cfg::ROW + Cfg::FEAT_LD + kAttnThreads);
 }
 
 // ------------------------------------------------------------------------------ backward
@@ -290,8 +377,10 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
   float* s_v = s_D + C * HW;               // 3*ROW saved attention vectors
   float* s_w = s_v + 3 * Cfg::ROW;         // 4*ROW work vectors
   float* s_dfeat = s_w + 4 * Cfg::ROW;     // FEAT_LD
-  float* s_ds = s_dfeat + Cfg::FEAT_LD;    // classes (rounded up by the launcher)
-  unsigned char* s_arg = reinterpret_cast<unsigned char*>(s_ds + ((classes + 3) / 4) * 4);  // C*HW
+  float* s_part = s_dfeat + Cfg::FEAT_LD;  // kAttnThreads partials of the split matrix-vector products
+  float* s_ds = s_part + kAttnThreads;     // classes (rounded up by the launcher)
+  float* s_zarg = s_ds + ((classes + 3) / 4) * 4;                                            // POOL: C*HW conv outputs at the arg-max
+  unsigned char* s_arg = reinterpret_cast<unsigned char*>(s_zarg + (POOL ? C * HW : 0));     // POOL: C*HW arg-max slots
 
   const int b = blockIdx.x, g = blockIdx.y, G = gridDim.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -304,27 +393,23 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
   // conv output of this crop and the upstream gradient of its gated feature map, one bulk copy each
   const float* dsrc = dout ? dout + ((size_t)b * G + g) * C * HW : nullptr;
   const float* zg = z + ((size_t)b * G + g) * C * HWPRE;
-  if (!POOL) attn_stage_in(&stage_bar, s_r, zg, C * HWPRE, s_D, dsrc, C * HW);
-  else if (dsrc != nullptr) attn_stage_in(&stage_bar, s_D, dsrc, C * HW, nullptr, nullptr, 0);
-  build_r<C, SPRE, POOL>(zg, sc, sh, s_r, POOL ? s_arg : nullptr);
-
+  // small per-crop vectors first: their loads travel while the bulk copies are in flight
   const float* att_row = att + ((size_t)b * G + g) * Cfg::ATT_LD;
   for (int i = tid; i < 3 * Cfg::ROW; i += kAttnThreads) s_v[i] = __ldg(att_row + i);
   const float* dsc = dscores.p[g];
   const bool has_head = (dsc != nullptr) && (prm.fc_w[g] != nullptr);
   if (has_head)
     for (int i = tid; i < classes; i += kAttnThreads) s_ds[i] = __ldg(dsc + (size_t)b * classes + i);
-  __syncthreads();
+  if (!POOL) attn_stage_in(&stage_bar, s_r, zg, C * HWPRE, s_D, dsrc, C * HW);
+  else if (dsrc != nullptr) attn_stage_in(&stage_bar, s_D, dsrc, C * HW, nullptr, nullptr, 0);
+  build_r<C, SPRE, POOL>(zg, sc, sh, s_r, POOL ? s_arg : nullptr, POOL ? s_zarg : nullptr);   // ends with a barrier
 
   const int F = (btype == BR_SPECTRAL) ? C : (btype == BR_SPATIAL ? 4 * C : (has_head ? C * HW : 0));
   // gradient of the head features: dfeat = Wc^T dscores   (Classifier, Hang2020.py:64)
-  for (int f = tid; f < F; f += kAttnThreads) {
-    float a = 0.f;
-    if (has_head) {
-      const float* fw = prm.fc_w[g];
-      for (int cls = 0; cls < classes; ++cls) a = fmaf(s_ds[cls], __ldg(fw + (size_t)cls * F + f), a);
-    }
-    s_dfeat[f] = a;
+  if (has_head) {
+    fc_cols(prm.fc_w[g], F, classes, s_ds, s_dfeat, s_part);
+  } else {
+    for (int f = tid; f < F; f += kAttnThreads) s_dfeat[f] = 0.f;
   }
   // upstream gradient of the gated feature map from the next conv's dgrad: already staged; zero when absent
   if (dsrc == nullptr)
@@ -337,37 +422,41 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
     const float* s_g = s_v; const float* s_h = s_v + Cfg::ROW; const float* s_s = s_v + 2 * Cfg::ROW;
     float* s_dsv = s_w; float* s_du2 = s_w + Cfg::ROW; float* s_du1 = s_w + 2 * Cfg::ROW; float* s_dg = s_w + 3 * Cfg::ROW;
     (void)s_g;
-    // D += dfeat/HW (mean over HW, global_spectral_pool :7-12);  ds[c] = sum_p D*r
-    for (int c = warp; c < C; c += kAttnThreads / 32) {
-      const float df = s_dfeat[c] / (float)HW;
-      float a = 0.f;
-      for (int p = lane; p < HW; p += 32) {
-        const float d = s_D[c * HW + p] + df;
-        s_D[c * HW + p] = d;
-        a = fmaf(d, s_r[c * HW + p], a);
+    // D += dfeat/HW (mean over HW, global_spectral_pool :7-12);  ds[c] = sum_p D*r;  du2 = ds * s(1-s)
+    if (HW <= 32) {
+      for (int c = tid; c < C; c += kAttnThreads) {
+        const float df = s_dfeat[c] / (float)HW;
+        float a = 0.f;
+#pragma unroll
+        for (int p = 0; p < HW; ++p) {
+          const float d = s_D[c * HW + p] + df;
+          s_D[c * HW + p] = d;
+          a = fmaf(d, s_r[c * HW + p], a);
+        }
+        const float sv = s_s[c];
+        s_du2[c] = a * sv * (1.f - sv);
       }
-      a = warp_sum(a);
-      if (lane == 0) s_dsv[c] = a;
+    } else {
+      for (int c = warp; c < C; c += kAttnThreads / 32) {
+        const float df = s_dfeat[c] / (float)HW;
+        float a = 0.f;
+        for (int p = lane; p < HW; p += 32) {
+          const float d = s_D[c * HW + p] + df;
+          s_D[c * HW + p] = d;
+          a = fmaf(d, s_r[c * HW + p], a);
+        }
+        a = warp_sum(a);
+        const float sv = s_s[c];
+        if (lane == 0) s_du2[c] = a * sv * (1.f - sv);
+      }
     }
+    (void)s_dsv;
     __syncthreads();
-    for (int i = tid; i < C; i += kAttnThreads) {
-      const float sv = s_s[i];
-      s_du2[i] = s_dsv[i] * sv * (1.f - sv);
-    }
+    fc_cols(prm.w1d[g], C, C, s_du2, s_du1, s_part);
+    if (tid < C) s_du1[tid] = (s_h[tid] > 0.f) ? s_du1[tid] : 0.f;
     __syncthreads();
-    for (int j = tid; j < C; j += kAttnThreads) {
-      float a = 0.f;
-      const float* w = prm.w1d[g];
-      for (int i = 0; i < C; ++i) a = fmaf(__ldg(w + i * C + j), s_du2[i], a);
-      s_du1[j] = (s_h[j] > 0.f) ? a : 0.f;
-    }
-    __syncthreads();
-    for (int j = tid; j < C; j += kAttnThreads) {
-      float a = 0.f;
-      const float* w = prm.w0d[g];
-      for (int i = 0; i < C; ++i) a = fmaf(__ldg(w + i * C + j), s_du1[i], a);
-      s_dg[j] = a / (float)HW;
-    }
+    fc_cols(prm.w0d[g], C, C, s_du1, s_dg, s_part);
+    if (tid < C) s_dg[tid] = s_dg[tid] / (float)HW;
     __syncthreads();
     for (int i = tid; i < C * HW; i += kAttnThreads) {
       const int c = i / HW;
@@ -396,6 +485,7 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
     // ds[p] = sum_c D*r ; dv2 = ds * s(1-s)
     for (int p = tid; p < HW; p += kAttnThreads) {
       float a = 0.f;
+#pragma unroll 8
       for (int c = 0; c < C; ++c) a = fmaf(s_D[c * HW + p], s_r[c * HW + p], a);
       const float sv = s_s[p];
       s_dv2[p] = a * sv * (1.f - sv);
@@ -455,13 +545,22 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
       }
       prow_row[e] = a;
     }
-    for (int c = warp; c < C; c += kAttnThreads / 32) {
-      float a = 0.f;
-      for (int p = lane; p < HW; p += 32) a = fmaf(s_dq[p], s_r[c * HW + p], a);
-      a = warp_sum(a);
-      if (lane == 0) prow_row[2 * KK + 2 + c] = a;
+    if (HW <= 32) {
+      for (int c = tid; c < C; c += kAttnThreads) {
+        float a = 0.f;
+#pragma unroll
+        for (int p = 0; p < HW; ++p) a = fmaf(s_dq[p], s_r[c * HW + p], a);
+        prow_row[2 * KK + 2 + c] = a;
+      }
+    } else {
+      for (int c = warp; c < C; c += kAttnThreads / 32) {
+        float a = 0.f;
+        for (int p = lane; p < HW; p += 32) a = fmaf(s_dq[p], s_r[c * HW + p], a);
+        a = warp_sum(a);
+        if (lane == 0) prow_row[2 * KK + 2 + c] = a;
+      }
     }
-    if (warp == 0) {
+    if (warp == kAttnThreads / 32 - 1) {
       float a = 0.f;
       for (int p = lane; p < HW; p += 32) a += s_dq[p];
       a = warp_sum(a);
@@ -483,49 +582,71 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
   // route through max-pool (argmax) and ReLU; emit da and the BatchNorm-backward partials
   float* da_out = da + ((size_t)b * G + g) * C * HWPRE;
   float* bn_row = bnrow + ((size_t)b * G + g) * 2 * C;
-  for (int c = warp; c < C; c += kAttnThreads / 32) {
-    const float scv = __ldg(sc + c), shv = __ldg(sh + c);
-    const float mu = __ldg(mean + g * C + c), is = __ldg(istd + g * C + c);
-    float s1 = 0.f, s2 = 0.f;
-    if (POOL) {
-      // one lane per pooled cell: only the arg-max position of its 2x2 window receives gradient
-      for (int e = lane; e < 2 * SPRE - 1; e += 32) {      // row / column dropped by the floor pooling
-        const int idx = e < SPRE ? (SPRE - 1) * SPRE + e : (e - SPRE) * SPRE + (SPRE - 1);
-        da_out[c * HWPRE + idx] = 0.f;
-      }
-      for (int cell = lane; cell < HW; cell += 32) {
-        const int cy = cell / S, cx = cell - cy * S;
-        const int base = c * HWPRE + (2 * cy) * SPRE + 2 * cx;
-        const int arg = s_arg[c * HW + cell];
-        const float zv = __ldg(zg + base + (arg >> 1) * SPRE + (arg & 1));
-        const float dv = fmaf(zv, scv, shv) > 0.f ? s_D[c * HW + cell] : 0.f;
-        da_out[base] = arg == 0 ? dv : 0.f;
-        da_out[base + 1] = arg == 1 ? dv : 0.f;
-        da_out[base + SPRE] = arg == 2 ? dv : 0.f;
-        da_out[base + SPRE + 1] = arg == 3 ? dv : 0.f;
-        s1 += dv;
-        s2 = fmaf(dv, (zv - mu) * is, s2);
-      }
-    } else {
-      for (int pp = lane; pp < HWPRE; pp += 32) {
-        const float zv = __ldg(zg + c * HWPRE + pp);     // second read of z (L2-resident), instead of keeping it in smem
-        const float dv = fmaf(zv, scv, shv) > 0.f ? s_D[c * HW + pp] : 0.f;
-        da_out[c * HWPRE + pp] = dv;
-        s1 += dv;
-        s2 = fmaf(dv, (zv - mu) * is, s2);
-      }
+  if (POOL) {
+    // One thread per pooled cell: only the arg-max position of its 2x2 window receives gradient.  The ReLU mask is r > 0
+    // (r is the rectified maximum itself) and the conv output at the arg-max was kept by build_r: no second read of z.
+    // Per-cell terms of the BatchNorm sums go back to shared memory (s_D: dv, s_r: dv * zhat) and are added per channel
+    // by one thread each, in cell order.
+    for (int e = tid; e < C * (2 * SPRE - 1); e += kAttnThreads) {   // row / column dropped by the floor pooling
+      const int c = e / (2 * SPRE - 1), k = e - c * (2 * SPRE - 1);
+      const int idx = k < SPRE ? (SPRE - 1) * SPRE + k : (k - SPRE) * SPRE + (SPRE - 1);
+      da_out[c * HWPRE + idx] = 0.f;
     }
-    s1 = warp_sum(s1);
-    s2 = warp_sum(s2);
-    if (lane == 0) { bn_row[c] = s1; bn_row[C + c] = s2; }
+    for (int i = tid; i < C * HW; i += kAttnThreads) {
+      const int c = i / HW, cell = i - c * HW;
+      const int cy = cell / S, cx = cell - cy * S;
+      const int base = c * HWPRE + (2 * cy) * SPRE + 2 * cx;
+      const int arg = s_arg[i];
+      const float dv = s_r[i] > 0.f ? s_D[i] : 0.f;
+      da_out[base] = arg == 0 ? dv : 0.f;
+      da_out[base + 1] = arg == 1 ? dv : 0.f;
+      da_out[base + SPRE] = arg == 2 ? dv : 0.f;
+      da_out[base + SPRE + 1] = arg == 3 ? dv : 0.f;
+      s_D[i] = dv;
+      s_r[i] = dv * ((s_zarg[i] - __ldg(mean + g * C + c)) * __ldg(istd + g * C + c));
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += kAttnThreads) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 5
+      for (int cell = 0; cell < HW; ++cell) { s1 += s_D[c * HW + cell]; s2 += s_r[c * HW + cell]; }
+      bn_row[c] = s1;
+      bn_row[C + c] = s2;
+    }
+  } else {
+    for (int c = warp; c < C; c += kAttnThreads / 32) {
+      const float mu = __ldg(mean + g * C + c), is = __ldg(istd + g * C + c);
+      constexpr int NIT = (HWPRE + 31) / 32;
+      float zv[NIT];
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {      // second read of z (L2-resident) instead of keeping it in smem; all loads first
+        const int pp = lane + 32 * it;
+        zv[it] = pp < HWPRE ? __ldg(zg + c * HWPRE + pp) : 0.f;
+      }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int pp = lane + 32 * it;
+        if (pp < HWPRE) {
+          const float dv = s_r[c * HW + pp] > 0.f ? s_D[c * HW + pp] : 0.f;   // r = relu(bn(z)) > 0  <=>  bn(z) > 0
+          da_out[c * HWPRE + pp] = dv;
+          s1 += dv;
+          s2 = fmaf(dv, (zv[it] - mu) * is, s2);
+        }
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      if (lane == 0) { bn_row[c] = s1; bn_row[C + c] = s2; }
+    }
   }
 }
 
 template <int C, int SPRE, bool POOL>
 size_t attn_bwd_smem(int classes) {
   using Cfg = AttnCfg<C, SPRE, POOL>;
-  const size_t floats = (size_t)2 * C * Cfg::HW + 7 * Cfg::ROW + Cfg::FEAT_LD + ((classes + 3) / 4) * 4;
-  return floats * sizeof(float) + (size_t)C * Cfg::HW;
+  const size_t floats = (size_t)2 * C * Cfg::HW + 7 * Cfg::ROW + Cfg::FEAT_LD + kAttnThreads + ((classes + 3) / 4) * 4 +
+                        (POOL ? (size_t)C * Cfg::HW : 0);
+  return floats * sizeof(float) + (POOL ? (size_t)C * Cfg::HW : 0);
 }
 
 }  // namespace dta
