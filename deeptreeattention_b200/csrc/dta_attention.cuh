@@ -82,9 +82,19 @@ __device__ __forceinline__ void build_r(const float* __restrict__ zsrc, const fl
     }
   } else {
     const int lane = tid & 31, warp = tid >> 5;
-    for (int c = warp; c < C; c += kAttnThreads / 32) {
-      const float sc = __ldg(scale + c), sh = __ldg(shift + c);
-      for (int p = lane; p < Cfg::HW; p += 32) s_r[c * Cfg::HW + p] = fmaxf(fmaf(s_r[c * Cfg::HW + p], sc, sh), 0.f);
+    constexpr int NW = kAttnThreads / 32, NC = (C + NW - 1) / NW;   // channels per warp
+    float scv[NC], shv[NC];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = warp + k * NW;
+      scv[k] = c < C ? __ldg(scale + c) : 0.f;
+      shv[k] = c < C ? __ldg(shift + c) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const int c = warp + k * NW;
+      if (c < C)
+        for (int p = lane; p < Cfg::HW; p += 32) s_r[c * Cfg::HW + p] = fmaxf(fmaf(s_r[c * Cfg::HW + p], scv[k], shv[k]), 0.f);
     }
   }
   __syncthreads();
@@ -99,7 +109,7 @@ __device__ __forceinline__ void fc_cols(const float* __restrict__ w, int nout, i
   if (nout >= kAttnThreads) {
     for (int i = tid; i < nout; i += kAttnThreads) {
       float a = 0.f;
-#pragma unroll 8
+#pragma unroll 16
       for (int j = 0; j < nin; ++j) a = fmaf(__ldg(w + (size_t)j * nout + i), s_vec[j], a);
       s_out[i] = a;
     }
@@ -111,7 +121,7 @@ __device__ __forceinline__ void fc_cols(const float* __restrict__ w, int nout, i
   const int i = tid & (nout - 1), q = tid / nout;
   const int j0 = q * per, j1 = min(nin, j0 + per);
   float a = 0.f;
-#pragma unroll 8
+#pragma unroll 16
   for (int j = j0; j < j1; ++j) a = fmaf(__ldg(w + (size_t)j * nout + i), s_vec[j], a);
   s_part[tid] = a;
   __syncthreads();
@@ -318,6 +328,7 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
       const float* w1 = v1 ? w0 + (size_t)NW * F : w0;
       const float* w2 = v2 ? w0 + (size_t)2 * NW * F : w0;
       const float* w3 = v3 ? w0 + (size_t)3 * NW * F : w0;
+#pragma unroll 4
       for (int f = lane; f < F; f += 32) {
         const float x = s_feat[f];
         a[0] = fmaf(x, __ldg(w0 + f), a[0]);
@@ -577,6 +588,8 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
     if (has_head)
       for (int i = tid; i < C * HW; i += kAttnThreads) s_D[i] += s_dfeat[i];
   }
+  if (POOL)   // BatchNorm mean / inverse std of this branch's channels for the per-cell loop below (s_part is idle by now)
+    for (int i = tid; i < C; i += kAttnThreads) { s_part[i] = __ldg(mean + g * C + i); s_part[C + i] = __ldg(istd + g * C + i); }
   __syncthreads();
 
   // route through max-pool (argmax) and ReLU; emit da and the BatchNorm-backward partials
@@ -603,7 +616,7 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
       da_out[base + SPRE] = arg == 2 ? dv : 0.f;
       da_out[base + SPRE + 1] = arg == 3 ? dv : 0.f;
       s_D[i] = dv;
-      s_r[i] = dv * ((s_zarg[i] - __ldg(mean + g * C + c)) * __ldg(istd + g * C + c));
+      s_r[i] = dv * ((s_zarg[i] - s_part[c]) * s_part[C + c]);
     }
     __syncthreads();
     for (int c = tid; c < C; c += kAttnThreads) {
