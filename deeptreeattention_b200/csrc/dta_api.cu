@@ -257,7 +257,7 @@ cudaError_t launch_fprop(const ConvSrc& src, const float* wp, Ptr2 bias, int bia
   if (e != cudaSuccess) return e;
   dim3 grid((B + NCROP - 1) / NCROP, G);
   if (nblk) *nblk = grid.x;
-  kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>(src, wp, bias, bias_split, out, out_ctot, stats, B);
+  launch_k(kern, grid, Cfg::NT, Cfg::SMEM_BYTES, st, src, wp, bias, bias_split, out, out_ctot, stats, B);
   return cudaGetLastError();
 }
 
@@ -269,7 +269,7 @@ cudaError_t launch_wgrad(const ConvSrc& in, const ConvSrc& dz, float* part, int 
   cudaError_t e = allow_smem(kern, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return e;
   dim3 grid((in.cin + CIK - 1) / CIK, nsplit, G);
-  kern<<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>(in, dz, part, B, per);
+  launch_k(kern, grid, Cfg::NT, Cfg::SMEM_BYTES, st, in, dz, part, B, per);
   return cudaGetLastError();
 }
 
@@ -286,7 +286,7 @@ cudaError_t run_tc_fprop(dta_ctx* ctx, cudaStream_t st, const __nv_bfloat16* xp,
   const int nwork = ntiles * G;
   const int grid = nwork < ctx->sm_count ? nwork : ctx->sm_count;
   if (nblk) *nblk = grid * 4;
-  kern<<<grid, kTcFpropThreads + (FUSEX ? 32 * kTcConvWarps : 0), Cfg::SMEM_BYTES, st>>>(xp, rows, nchunk, chunks_per_group, wp, nstage, bias,
+  launch_k(kern, grid, kTcFpropThreads + (FUSEX ? 32 * kTcConvWarps : 0), Cfg::SMEM_BYTES, st, xp, rows, nchunk, chunks_per_group, wp, nstage, bias,
                                                                                          bias_split, out, out_ctot, cout_g, B, ntiles, G, stats, fx);
   return cudaGetLastError();
 }
@@ -296,7 +296,7 @@ cudaError_t run_tc_wgrad(cudaStream_t st, const __nv_bfloat16* dzp, int dz_chunk
   auto kern = tc_conv_wgrad_kernel<S, Cfg>;
   cudaError_t e = allow_smem(kern, Cfg::SMEM_BYTES);
   if (e != cudaSuccess) return e;
-  kern<<<dim3(sp.nslices * Cfg::NTG, sp.nsplit, G), kTcThreads, Cfg::SMEM_BYTES, st>>>(dzp, dz_chunks, xp, x_chunks, rows, cin_g, cout_g, sp.nkstage,
+  launch_k(kern, dim3(sp.nslices * Cfg::NTG, sp.nsplit, G), kTcThreads, Cfg::SMEM_BYTES, st, dzp, dz_chunks, xp, x_chunks, rows, cin_g, cout_g, sp.nkstage,
                                                                           sp.per, part);
   return cudaGetLastError();
 }
@@ -306,10 +306,10 @@ cudaError_t run_tc_pack(dta_ctx* ctx, cudaStream_t st, const ConvSrc& src, int G
   size_t blocks = (total + 255) / 256;
   if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
   const int grid = (int)blocks;
-  if (src.mode == SRC_RAW) tc_pack_stream_kernel<S, SRC_RAW, false><<<grid, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
-  else if (src.mode == SRC_DZ) tc_pack_stream_kernel<S, SRC_DZ, false><<<grid, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
-  else if (src.pool) tc_pack_stream_kernel<S, SRC_ACT, true><<<grid, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
-  else tc_pack_stream_kernel<S, SRC_ACT, false><<<grid, 256, 0, st>>>(src, G, B, nchunk, rows, dst);
+  if (src.mode == SRC_RAW) launch_k(tc_pack_stream_kernel<S, SRC_RAW, false>, grid, 256, 0, st, src, G, B, nchunk, rows, dst);
+  else if (src.mode == SRC_DZ) launch_k(tc_pack_stream_kernel<S, SRC_DZ, false>, grid, 256, 0, st, src, G, B, nchunk, rows, dst);
+  else if (src.pool) launch_k(tc_pack_stream_kernel<S, SRC_ACT, true>, grid, 256, 0, st, src, G, B, nchunk, rows, dst);
+  else launch_k(tc_pack_stream_kernel<S, SRC_ACT, false>, grid, 256, 0, st, src, G, B, nchunk, rows, dst);
   return cudaGetLastError();
 }
 ConvSrc src_raw(const float* x, int cin, int hw) {
@@ -477,6 +477,10 @@ int dta_set_option(dta_ctx* ctx, const char* key, int64_t value) {
     ctx->overlap = value != 0;
     return DTA_OK;
   }
+  if (!strcmp(key, "pdl")) {
+    ctx->pdl = value != 0;
+    return DTA_OK;
+  }
   return fail(ctx, DTA_ERR_INVALID_ARG, std::string("unknown option ") + key);
 }
 
@@ -487,6 +491,7 @@ int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value) {
   if (!strcmp(key, "profile")) { *value = ctx->profile; return DTA_OK; }
   if (!strcmp(key, "sm_count")) { *value = ctx->sm_count; return DTA_OK; }
   if (!strcmp(key, "overlap")) { *value = ctx->overlap; return DTA_OK; }
+  if (!strcmp(key, "pdl")) { *value = ctx->pdl; return DTA_OK; }
   if (!strcmp(key, "fuse_x")) { *value = ctx->fuse_x; return DTA_OK; }
   return DTA_ERR_INVALID_ARG;
 }
@@ -520,6 +525,7 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
   ctx->launches = 0;
+  pdl_enabled() = ctx->pdl;
 
   const int B = shape->batch, nb = d.nb, bands = shape->bands, classes = shape->classes;
   const bool vanilla = shape->net_kind == DTA_NET_VANILLA;
@@ -538,30 +544,30 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
   for (int k = 0; k < 3 && ctx->conv_impl == 0; ++k) {
     Ptr2 w{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}};
     const int cin = k == 0 ? bands : kC[k - 1];
-    pack_conv_w_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, kC[k], cin, k == 0 ? 1 : 0, L.wp[k]);
+    launch_k(pack_conv_w_kernel, ctx->sm_count * 2, 256, 0, st, w, nb, kC[k], cin, k == 0 ? 1 : 0, L.wp[k]);
     DTA_CHECK_LAUNCH(ctx, "pack_conv_w");
   }
   for (int g = 0; g < nb; ++g) {
     if (d.btype[g] != BR_SPECTRAL) continue;
     for (int k = 0; k < 3; ++k) {
       const int ks = k == 0 ? 3 : (k == 1 ? 5 : 7);  // Hang2020.py:136-141
-      pack_spectral_kernel<<<(kC[k] * kC[k] + 255) / 256, 256, 0, ss>>>(params->branch[g].attn[k].w0, kC[k], ks, L.spec_pack[g][k][0], L.spec_pack[g][k][1]);
+      launch_k(pack_spectral_kernel, (kC[k] * kC[k] + 255) / 256, 256, 0, ss, params->branch[g].attn[k].w0, kC[k], ks, L.spec_pack[g][k][0], L.spec_pack[g][k][1]);
       DTA_CHECK_LAUNCH(ctx, "pack_spectral");
-      pack_spectral_kernel<<<(kC[k] * kC[k] + 255) / 256, 256, 0, ss>>>(params->branch[g].attn[k].w1, kC[k], ks, L.spec_pack[g][k][2], L.spec_pack[g][k][3]);
+      launch_k(pack_spectral_kernel, (kC[k] * kC[k] + 255) / 256, 256, 0, ss, params->branch[g].attn[k].w1, kC[k], ks, L.spec_pack[g][k][2], L.spec_pack[g][k][3]);
       DTA_CHECK_LAUNCH(ctx, "pack_spectral");
     }
   }
   auto conv_w = [&](int k) { return Ptr2{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}}; };
   auto conv_b = [&](int k) { return Ptr2{{params->branch[0].conv[k].conv_b, nb > 1 ? params->branch[1].conv[k].conv_b : nullptr}}; };
   if (tcp) {
-    tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, ss>>>(conv_w(1), nb, 64, 32, 2, 1, W.wpf[1]);
+    launch_k(tc_pack_w_fprop_kernel<64>, ctx->sm_count, 256, 0, ss, conv_w(1), nb, 64, 32, 2, 1, W.wpf[1]);
     DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
-    tc_pack_w_fprop_kernel<128><<<ctx->sm_count, 256, 0, ss>>>(conv_w(2), nb, 128, 64, 4, 1, W.wpf[2]);
+    launch_k(tc_pack_w_fprop_kernel<128>, ctx->sm_count, 256, 0, ss, conv_w(2), nb, 128, 64, 4, 1, W.wpf[2]);
     DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
     if (!vanilla) {   // the attention kernels write the crop rows of a1p / a2p; the guard and tail rows are zeroed here
-      tc_zero_guards_kernel<<<32, 256, 0, ss>>>(L.a1p, tg.rows11, nb * 4, (size_t)B * Stream<11>::PC);
+      launch_k(tc_zero_guards_kernel, 32, 256, 0, ss, L.a1p, tg.rows11, nb * 4, (size_t)B * Stream<11>::PC);
       DTA_CHECK_LAUNCH(ctx, "tc_zero_guards");
-      tc_zero_guards_kernel<<<32, 256, 0, ss>>>(L.a2p, tg.rows5, nb * 8, (size_t)B * Stream<5>::PC);
+      launch_k(tc_zero_guards_kernel, 32, 256, 0, ss, L.a2p, tg.rows5, nb * 8, (size_t)B * Stream<5>::PC);
       DTA_CHECK_LAUNCH(ctx, "tc_zero_guards");
     }
   }
@@ -575,7 +581,7 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
     {
       StageScope sc(ctx, "fwd.conv1_pack", st);
       if (!ctx->fuse_x) DTA_TC_CHECK(run_tc_pack<11>(ctx, st, src_raw(x, bands, kHW), 1, B, tg.nchunk1, tg.rows11, L.xp), "tc_pack_stream(x)");
-      tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, st>>>(conv_w(0), nb, 32, bands, tg.nstage1, 0, W.wpf[0]);
+      launch_k(tc_pack_w_fprop_kernel<64>, ctx->sm_count, 256, 0, st, conv_w(0), nb, 32, bands, tg.nstage1, 0, W.wpf[0]);
       DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
     }
     {
@@ -609,7 +615,7 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
   auto bn_finalize = [&](int k, int nblk_k) -> int {
     StageScope sc(ctx, "fwd.bn_finalize", st);
     const int ctot = nb * kC[k];
-    bn_fwd_finalize_kernel<<<(ctot + kBnCh - 1) / kBnCh, kBnCh * kBnSlices, 0, st>>>(W.stats, nblk_k, ctot, (double)B * kHWpre[k], bn_params(params, d, k),
+    launch_k(bn_fwd_finalize_kernel, (ctot + kBnCh - 1) / kBnCh, kBnCh * kBnSlices, 0, st, W.stats, nblk_k, ctot, (double)B * kHWpre[k], bn_params(params, d, k),
                                                                     shape->training, L.bn_mean[k], L.bn_istd[k], L.bn_scale[k], L.bn_shift[k]);
     DTA_CHECK_LAUNCH(ctx, "bn_fwd_finalize");
     return DTA_OK;
@@ -627,7 +633,7 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
     auto kern = attn_fwd_kernel<32, 11, false>;
     const size_t sm = attn_fwd_smem<32, 11, false>();
     allow_smem(kern, sm);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], attn_params(params, L, d, 0, false, classes_second), classes, L.att[0], L.feat[0], score_ptrs(0),
+    launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[0], L.bn_scale[0], L.bn_shift[0], attn_params(params, L, d, 0, false, classes_second), classes, L.att[0], L.feat[0], score_ptrs(0),
                                               tcp ? L.a1p : nullptr, tg.rows11, nb * 4);
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<1>");
   }
@@ -658,7 +664,7 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
     auto kern = attn_fwd_kernel<64, 11, true>;
     const size_t sm = attn_fwd_smem<64, 11, true>();
     allow_smem(kern, sm);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], attn_params(params, L, d, 1, false, classes_second), classes, L.att[1], L.feat[1], score_ptrs(1),
+    launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[1], L.bn_scale[1], L.bn_shift[1], attn_params(params, L, d, 1, false, classes_second), classes, L.att[1], L.feat[1], score_ptrs(1),
                                               tcp ? L.a2p : nullptr, tg.rows5, nb * 8);
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<2>");
   }
@@ -688,14 +694,14 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
     auto kern = attn_fwd_kernel<128, 5, true>;
     const size_t sm = attn_fwd_smem<128, 5, true>();
     allow_smem(kern, sm);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], attn_params(params, L, d, 2, vanilla, classes_second), classes, L.att[2], L.feat[2], score_ptrs(2), nullptr, 0, 0);
+    launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[2], L.bn_scale[2], L.bn_shift[2], attn_params(params, L, d, 2, vanilla, classes_second), classes, L.att[2], L.feat[2], score_ptrs(2), nullptr, 0, 0);
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<3>");
   }
   // 5. alpha blend + copies of the last-head scores for dalpha
   if (shape->net_kind == DTA_NET_HANG2020) {
     StageScope sc(ctx, "fwd.joint", st);
     const size_t n = (size_t)B * classes;
-    joint_fwd_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(scores[2], scores[5], params->alpha, joint, n);
+    launch_k(joint_fwd_kernel, (int)((n + 255) / 256), 256, 0, st, scores[2], scores[5], params->alpha, joint, n);
     DTA_CHECK_LAUNCH(ctx, "joint_fwd");
     cudaMemcpyAsync(L.s3[0], scores[2], n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(L.s3[1], scores[5], n * sizeof(float), cudaMemcpyDeviceToDevice, st);
@@ -730,8 +736,9 @@ int dta_preprocess_crops(dta_ctx* ctx, const int16_t* raw, int batch, int bands_
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
   ctx->launches = 0;
+  pdl_enabled() = ctx->pdl;
   StageScope sc(ctx, "data.preprocess_crops", st);
-  preprocess_crops_kernel<<<batch, 128 * kPrepSlices, 0, st>>>(reinterpret_cast<const short*>(raw), bands_in, kHW, clip, out);
+  launch_k(preprocess_crops_kernel, batch, 128 * kPrepSlices, 0, st, reinterpret_cast<const short*>(raw), bands_in, kHW, clip, out);
   DTA_CHECK_LAUNCH(ctx, "preprocess_crops");
   return DTA_OK;
 }
@@ -758,6 +765,7 @@ int dta_grad_allreduce(dta_ctx* ctx, int rank, int world, void* const peer_buffe
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
   ctx->launches = 0;
+  pdl_enabled() = ctx->pdl;
   StageScope sc(ctx, "dist.grad_allreduce", st);
   // every CTA spins on flags, so the grid must be co-resident: far below one CTA per SM
   int grid = (int)((n_float4 + kArThreads - 1) / kArThreads);
@@ -784,6 +792,7 @@ int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, c
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
   ctx->launches = 0;
+  pdl_enabled() = ctx->pdl;
   HeadPtrs h{};
   for (int i = 0; i < n_heads; ++i) {
     if (!scores[i]) return fail(ctx, DTA_ERR_INVALID_ARG, "scores[i] is NULL");
@@ -795,13 +804,13 @@ int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, c
   float* rows = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   StageScope sc(ctx, "loss.cross_entropy", st);
   cudaMemsetAsync(bad, 0, sizeof(int), st);
-  ce_den_kernel<<<1, 256, 0, st>>>(reinterpret_cast<const long long*>(labels), class_weight, batch, classes, den, bad);
+  launch_k(ce_den_kernel, 1, 256, 0, st, reinterpret_cast<const long long*>(labels), class_weight, batch, classes, den, bad);
   DTA_CHECK_LAUNCH(ctx, "ce_den");
   const long long warps = (long long)n_heads * batch;
-  ce_rows_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(h, n_heads, reinterpret_cast<const long long*>(labels), class_weight, batch,
+  launch_k(ce_rows_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, st, h, n_heads, reinterpret_cast<const long long*>(labels), class_weight, batch,
                                                                      classes, den, rows);
   DTA_CHECK_LAUNCH(ctx, "ce_rows");
-  ce_finish_kernel<<<1, 256, 0, st>>>(rows, n_heads, batch, den, loss);
+  launch_k(ce_finish_kernel, 1, 256, 0, st, rows, n_heads, batch, den, loss);
   DTA_CHECK_LAUNCH(ctx, "ce_finish");
   return DTA_OK;
 }
@@ -823,6 +832,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
   ctx->launches = 0;
+  pdl_enabled() = ctx->pdl;
 
   const int B = shape->batch, nb = d.nb, bands = shape->bands, classes = shape->classes;
   const bool vanilla = shape->net_kind == DTA_NET_VANILLA;
@@ -845,11 +855,11 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   for (int h = 0; h < d.n_heads; ++h) dS[h] = dscores[h];
   StageScope pre_scope(ctx, "bwd.prologue", st);
   if (hang && djoint) {
-    joint_bwd_kernel<<<(int)((nsc + 255) / 256), 256, 0, st>>>(dscores[2], dscores[5], djoint, params->alpha, W.dS[2], W.dS[5], nsc);
+    launch_k(joint_bwd_kernel, (int)((nsc + 255) / 256), 256, 0, st, dscores[2], dscores[5], djoint, params->alpha, W.dS[2], W.dS[5], nsc);
     DTA_CHECK_LAUNCH(ctx, "joint_bwd");
     dS[2] = W.dS[2]; dS[5] = W.dS[5];
     if (grads->alpha) {
-      alpha_grad_kernel<<<1, 1024, 0, st>>>(djoint, L.s3[0], L.s3[1], params->alpha, nsc, grads->alpha);
+      launch_k(alpha_grad_kernel, 1, 1024, 0, st, djoint, L.s3[0], L.s3[1], params->alpha, nsc, grads->alpha);
       DTA_CHECK_LAUNCH(ctx, "alpha_grad");
     }
   } else if (hang && grads->alpha) {
@@ -866,16 +876,16 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   for (int k = 1; k < 3; ++k) {
     Ptr2 w{{params->branch[0].conv[k].conv_w, nb > 1 ? params->branch[1].conv[k].conv_w : nullptr}};
     if (tcp) {
-      if (k == 1) tc_pack_w_fprop_kernel<32><<<ctx->sm_count, 256, 0, ss>>>(w, nb, 64, 32, 4, 2, W.wdp[0]);
-      else tc_pack_w_fprop_kernel<64><<<ctx->sm_count, 256, 0, ss>>>(w, nb, 128, 64, 8, 2, W.wdp[1]);
+      if (k == 1) launch_k(tc_pack_w_fprop_kernel<32>, ctx->sm_count, 256, 0, ss, w, nb, 64, 32, 4, 2, W.wdp[0]);
+      else launch_k(tc_pack_w_fprop_kernel<64>, ctx->sm_count, 256, 0, ss, w, nb, 128, 64, 8, 2, W.wdp[1]);
     } else {
-      pack_conv_wd_kernel<<<ctx->sm_count * 2, 256, 0, ss>>>(w, nb, kC[k], kC[k - 1], 0, W.wd[k]);
+      launch_k(pack_conv_wd_kernel, ctx->sm_count * 2, 256, 0, ss, w, nb, kC[k], kC[k - 1], 0, W.wd[k]);
     }
     DTA_CHECK_LAUNCH(ctx, "pack_conv_wd");
   }
   if (dx) {
     Ptr2 w{{params->branch[0].conv[0].conv_w, nb > 1 ? params->branch[1].conv[0].conv_w : nullptr}};
-    pack_conv_wd_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(w, nb, 32, bands, 1, W.wd[0]);
+    launch_k(pack_conv_wd_kernel, ctx->sm_count * 2, 256, 0, st, w, nb, 32, bands, 1, W.wd[0]);
     DTA_CHECK_LAUNCH(ctx, "pack_conv_wd");
   }
 
@@ -908,7 +918,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   auto bn_bwd = [&](int k) -> int {
     StageScope sc(ctx, "bwd.bn_finalize", st);
     const int ctot = nb * kC[k];
-    bn_bwd_finalize_kernel<<<(ctot + kBnCh - 1) / kBnCh, kBnCh * kBnSlices, 0, st>>>(W.bnrows, B, nb, kC[k], (double)B * kHWpre[k], bn_params(params, d, k),
+    launch_k(bn_bwd_finalize_kernel, (ctot + kBnCh - 1) / kBnCh, kBnCh * kBnSlices, 0, st, W.bnrows, B, nb, kC[k], (double)B * kHWpre[k], bn_params(params, d, k),
                                                                     L.bn_mean[k], L.bn_istd[k], shape->training, bn_grads(k), W.k0[k], W.k1[k], W.k2[k]);
     DTA_CHECK_LAUNCH(ctx, "bn_bwd_finalize");
     return DTA_OK;
@@ -978,9 +988,9 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     if (tcp) {
       // tensor-core partials are [split][g][tap][ci][co]; conv1 is one group over both branches' output channels
       const int G = k == 0 ? 1 : nb, cout_g = k == 0 ? nb * kC[0] : kC[k];
-      tc_wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, ss>>>(W.wpart, nsplit, G, cout_g, cin, dw, per_branch);
+      launch_k(tc_wgrad_reduce_kernel, ctx->sm_count * 4, 256, 0, ss, W.wpart, nsplit, G, cout_g, cin, dw, per_branch);
     } else
-    wgrad_reduce_kernel<<<ctx->sm_count * 4, 256, 0, ss>>>(W.wpart, nsplit, 1, per_branch * nb, dw, per_branch);
+    launch_k(wgrad_reduce_kernel, ctx->sm_count * 4, 256, 0, ss, W.wpart, nsplit, 1, per_branch * nb, dw, per_branch);
     DTA_CHECK_LAUNCH(ctx, "wgrad_reduce");
     return DTA_OK;
   };
@@ -991,7 +1001,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     const size_t sm = attn_bwd_smem<128, 5, true>(classes);
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn3", st);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[2], L.bn_scale[2], L.bn_shift[2], L.bn_mean[2], L.bn_istd[2], attn_prm(2), classes, L.att[2], L.feat[2],
+    launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[2], L.bn_scale[2], L.bn_shift[2], L.bn_mean[2], L.bn_istd[2], attn_prm(2), classes, L.att[2], L.feat[2],
                                               ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow[2]);
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<3>");
@@ -1030,7 +1040,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     const size_t sm = attn_bwd_smem<64, 11, true>(classes);
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn2", st);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[1], L.bn_scale[1], L.bn_shift[1], L.bn_mean[1], L.bn_istd[1], attn_prm(1), classes, L.att[1], L.feat[1],
+    launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[1], L.bn_scale[1], L.bn_shift[1], L.bn_mean[1], L.bn_istd[1], attn_prm(1), classes, L.att[1], L.feat[1],
                                               ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow[1]);
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<2>");
@@ -1068,7 +1078,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     const size_t sm = attn_bwd_smem<32, 11, false>(classes);
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn1", st);
-    kern<<<dim3(B, nb), kAttnThreads, sm, st>>>(L.z[0], L.bn_scale[0], L.bn_shift[0], L.bn_mean[0], L.bn_istd[0], attn_prm(0), classes, L.att[0], L.feat[0],
+    launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[0], L.bn_scale[0], L.bn_shift[0], L.bn_mean[0], L.bn_istd[0], attn_prm(0), classes, L.att[0], L.feat[0],
                                               ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow[0]);
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<1>");
@@ -1079,9 +1089,9 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
       side.wait_main();
       StageScope sc(ctx, "bwd.small_param_grads", ss);
       if (rtiles > reduce_tiles_bound(classes, nb)) return fail(ctx, DTA_ERR_UNSUPPORTED, "reduction tile bound exceeded");
-      batched_reduce_kernel<<<dim3(rtiles, kReduceSplits), 256, 0, ss>>>(rtab, B, W.rpart);
+      launch_k(batched_reduce_kernel, dim3(rtiles, kReduceSplits), 256, 0, ss, rtab, B, W.rpart);
       DTA_CHECK_LAUNCH(ctx, "batched_reduce");
-      batched_reduce_finish_kernel<<<rtiles, 256, 0, ss>>>(rtab, W.rpart);
+      launch_k(batched_reduce_finish_kernel, rtiles, 256, 0, ss, rtab, W.rpart);
       DTA_CHECK_LAUNCH(ctx, "batched_reduce_finish");
     }
     if ((rc = bn_bwd(0)) != DTA_OK) return rc;

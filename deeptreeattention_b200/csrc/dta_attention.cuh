@@ -176,6 +176,7 @@ attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __
                 MutPtr2 scores /*per branch [B][classes]*/,
                 __nv_bfloat16* __restrict__ packed /*split-bf16 position stream of the gated output (next conv's operand) or null*/,
                 size_t packed_rows, int packed_nchunk) {
+  pdl_prologue();
   using Cfg = AttnCfg<C, SPRE, POOL>;
   constexpr int S = Cfg::S, HW = Cfg::HW;
   extern __shared__ __align__(16) float smem[];
@@ -379,6 +380,7 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
                 Ptr2 dscores /*per branch [B][classes] or null*/, const float* __restrict__ dout /*[B][G][C][HW] or null*/,
                 float* __restrict__ da /*[B][G*C][HWPRE]*/, float* __restrict__ bnrow /*[B][G][2C]*/,
                 float* __restrict__ prow /*[B][G][ROW_LD]*/) {
+  pdl_prologue();
   using Cfg = AttnCfg<C, SPRE, POOL>;
   using Row = AttnBwdRow<C, SPRE, POOL>;
   constexpr int S = Cfg::S, HW = Cfg::HW, HWPRE = Cfg::HWPRE;

@@ -47,6 +47,15 @@ struct MutPtr2 {
   float* p[2];
 };
 
+// Programmatic dependent launch: first statement of every kernel.  launch_dependents lets the NEXT kernel of the stream be
+// scheduled as soon as every CTA of this grid has started (its CTAs then park in their own wait); wait blocks until the
+// PREVIOUS grid has completed and its writes are visible, so stream order is preserved exactly -- only the launch latency
+// between the ~60 short kernels of a step is hidden.  Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ float sigmoidf_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
 
 // Fetch conv input element (crop b, group g, channel ci within group, position p on an

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(FpropCfg<S, NCROP, TP, TC, COUT, CK>::NT)
 conv3x3_fprop_simt(ConvSrc src, const float* __restrict__ wp /*[G][Cin][9][COUT]*/, Ptr2 bias,
                    int bias_split /*channels per bias pointer*/, float* __restrict__ out, int out_ctot,
                    float* __restrict__ stats /*[gridDim.x][G*COUT][2] or null*/, int B) {
+  pdl_prologue();
   using Cfg = FpropCfg<S, NCROP, TP, TC, COUT, CK>;
   constexpr int PS = Cfg::PS, HW = Cfg::HW;
   extern __shared__ __align__(16) float smem[];
@@ -179,6 +180,7 @@ template <int S, int CIK, int COUT, int TCO>
 __global__ void __launch_bounds__(WgradCfg<S, CIK, COUT, TCO>::NT)
 conv3x3_wgrad_simt(ConvSrc in, ConvSrc dz, float* __restrict__ part /*[nsplit][G][COUT][Cin][9]*/, int B,
                    int crops_per_split) {
+  pdl_prologue();
   using Cfg = WgradCfg<S, CIK, COUT, TCO>;
   constexpr int PS = Cfg::PS, HW = Cfg::HW;
   extern __shared__ __align__(16) float smem[];
@@ -253,6 +255,7 @@ conv3x3_wgrad_simt(ConvSrc in, ConvSrc dz, float* __restrict__ part /*[nsplit][G
 // dW[g-th pointer][i] = sum_s part[s][g][i]   (fixed order)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int G, size_t per_group,
                                     MutPtr2 dw, size_t ptr_split /*elements per destination tensor*/) {
+  pdl_prologue();
   const size_t total = (size_t)G * per_group;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     float s = 0.f;

@@ -58,6 +58,7 @@ inline size_t tc_rows(int B, int pc, int tile) {
 template <int S, int MODE, bool POOL>
 __global__ void __launch_bounds__(256)
 tc_pack_stream_kernel(ConvSrc src, int G, int B, int nchunk, size_t rows, __nv_bfloat16* __restrict__ dst) {
+  pdl_prologue();
   using St = Stream<S>;
   const size_t total = rows * nchunk;
   const int ctot = G * src.cin;
@@ -141,6 +142,7 @@ tc_pack_stream_kernel(ConvSrc src, int G, int B, int nchunk, size_t rows, __nv_b
 // Zero the guard rows [0, GUARD) and the tail rows [GUARD + valid, rows) of every (half, chunk) plane of a packed stream
 // whose crop rows are written by another kernel (the attention kernels pack their own output).
 __global__ void tc_zero_guards_kernel(__nv_bfloat16* __restrict__ dst, size_t rows, int nchunk, size_t valid) {
+  pdl_prologue();
   const size_t tail0 = kTcGuard + valid;
   const size_t per_plane = kTcGuard + (rows - tail0);
   const size_t total = per_plane * nchunk * 2;
@@ -160,6 +162,7 @@ __global__ void tc_zero_guards_kernel(__nv_bfloat16* __restrict__ dst, size_t ro
 // w.p[br] = conv_layer.weight (cout_b, cin, 3, 3); rows / k beyond the tensor are zero.
 template <int NCO>
 __global__ void tc_pack_w_fprop_kernel(Ptr2 w, int nb, int cout_b, int cin, int nstage, int mode, __nv_bfloat16* __restrict__ dst) {
+  pdl_prologue();
   const int G = mode == 0 ? 1 : nb;
   const size_t per_group = (size_t)nstage * 9 * 2 * (2 * NCO) * 8;
   const size_t total = per_group * G;
@@ -235,6 +238,7 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
                      const __nv_bfloat16* __restrict__ wp /*[G][nstage][W_BYTES]*/, int nstage, Ptr2 bias, int bias_split,
                      float* __restrict__ out /*[B][out_ctot][S*S]*/, int out_ctot, int cout_g, int B, int ntiles, int G,
                      float* __restrict__ stats /*[gridDim.x*4][out_ctot][2] or null: BatchNorm partial sums of out*/, FuseX fx) {
+  pdl_prologue();
   using Cfg = TcFprop<S, NCO, ACC2>;
   using St = Stream<S>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -554,6 +558,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows][8]*/, int dz_chunks,
                      const __nv_bfloat16* __restrict__ xp /*[2][x_chunks][rows][8]*/, int x_chunks, size_t rows,
                      int cin_g, int cout_g, int nkstage_total, int stages_per_split, float* __restrict__ part /*[nsplit][G][cout_g][cin_g][9]*/) {
+  pdl_prologue();
   using St = Stream<S>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -693,6 +698,7 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows
 // reference's (cout, cin, 3, 3) tensor, or two of them when one group covers both branches (conv1).
 __global__ void tc_wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int G, int cout_g, int cin_g, MutPtr2 dw,
                                        size_t ptr_split /*elements per destination tensor*/) {
+  pdl_prologue();
   const size_t per_split = (size_t)G * 9 * cin_g * cout_g;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_split; i += (size_t)gridDim.x * blockDim.x) {
     float s = 0.f;

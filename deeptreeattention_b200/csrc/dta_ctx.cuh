@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "dta_common.cuh"
@@ -30,6 +31,7 @@ struct dta_ctx {
   // Side stream for work off the critical path (parameter packing, weight gradients): forked from / joined to the caller's
   // stream with the events below, so the caller still sees one stream-ordered call (and a CUDA-graph capture sees a DAG).
   int overlap = 1;
+  int pdl = 1;         // programmatic dependent launch between consecutive kernels (launch_k below)
   cudaStream_t side = nullptr;
   std::vector<cudaEvent_t> sync_events;
   size_t sync_next = 0;
@@ -95,6 +97,28 @@ inline void fold_spans(dta_ctx* ctx) {
 inline int fail(dta_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
   return code;
+}
+
+// Kernel launch with the programmatic-dependent-launch attribute (option "pdl"): consecutive kernels of a stream overlap
+// their launch latency; every kernel launched through here starts with pdl_prologue() (dta_common.cuh), which restores
+// exact stream order before it touches memory.  Captured into CUDA graphs as programmatic edges.
+inline int& pdl_enabled() {
+  static thread_local int v = 1;
+  return v;
+}
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
 }
 
 // Fork/join of the library-owned side stream around one C-ABI call (option "overlap").  Inactive (everything on the caller's

@@ -16,6 +16,7 @@ struct HeadPtrs {
 // den = sum_b w[y_b]  (fp64, fixed order; one block)
 __global__ void ce_den_kernel(const long long* __restrict__ y, const float* __restrict__ w, int B, int classes, double* __restrict__ den,
                               int* __restrict__ bad_label) {
+  pdl_prologue();
   __shared__ double s[256];
   double a = 0.0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -35,6 +36,7 @@ __global__ void ce_den_kernel(const long long* __restrict__ y, const float* __re
 // One warp per (head, crop): stable log-softmax, weighted NLL term and the score gradient.
 __global__ void ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restrict__ y, const float* __restrict__ w, int B, int classes,
                                const double* __restrict__ den, float* __restrict__ row_loss /*[n_heads][B]*/) {
+  pdl_prologue();
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= n_heads * B) return;
   const int head = gw / B, b = gw - head * B;
@@ -63,6 +65,7 @@ __global__ void ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restr
 
 // loss[head] = sum_b row_loss / den (fp64, fixed order), loss[n_heads] = sum over heads.  One block.
 __global__ void ce_finish_kernel(const float* __restrict__ row_loss, int n_heads, int B, const double* __restrict__ den, float* __restrict__ loss) {
+  pdl_prologue();
   __shared__ double s[256];
   __shared__ double total;
   if (threadIdx.x == 0) total = 0.0;

@@ -9,6 +9,7 @@ namespace dta {
 // Wp[g][ci][tap][co]: forward weight table.  merged=1: one group whose output channels are
 // the concatenation of both branches (conv1 reads the same crops for both branches).
 __global__ void pack_conv_w_kernel(Ptr2 w, int nb, int cout_b, int cin, int merged, float* __restrict__ wp) {
+  pdl_prologue();
   const size_t per = (size_t)cout_b * cin * 9;
   const size_t total = per * nb;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -28,6 +29,7 @@ __global__ void pack_conv_w_kernel(Ptr2 w, int nb, int cout_b, int cin, int merg
 // Wd[g][co][8-tap][ci]: the transposed + flipped table that turns the forward kernel into
 // the input-gradient kernel.  merged=1: single group with nb*cout_b "input" channels.
 __global__ void pack_conv_wd_kernel(Ptr2 w, int nb, int cout_b, int cin, int merged, float* __restrict__ wd) {
+  pdl_prologue();
   const size_t per = (size_t)cout_b * cin * 9;
   const size_t total = per * nb;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -47,6 +49,7 @@ __global__ void pack_conv_wd_kernel(Ptr2 w, int nb, int cout_b, int cin, int mer
 // sequence (Hang2020.py:146-147,155-158).  d[i*C+j] and its transpose t[j*C+i].
 __global__ void pack_spectral_kernel(const float* __restrict__ w, int C, int ks, float* __restrict__ d,
                                      float* __restrict__ t) {
+  pdl_prologue();
   const int total = C * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int r = i / C, c = i - r * C;
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(kBnCh * kBnSlices)
 bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int nblk, int ctot, double count, BnParams bn,
                        int training, float* __restrict__ mean, float* __restrict__ istd, float* __restrict__ scale,
                        float* __restrict__ shift) {
+  pdl_prologue();
   __shared__ double ss[kBnSlices * kBnCh / 32][kBnCh], sq[kBnSlices * kBnCh / 32][kBnCh];
   const int cx = threadIdx.x & (kBnCh - 1), ry = threadIdx.x / kBnCh;
   const int ch = blockIdx.x * kBnCh + cx;
@@ -141,6 +145,7 @@ __global__ void __launch_bounds__(kBnCh * kBnSlices)
 bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, int G, int C, double count, BnParams bn, const float* __restrict__ mean,
                        const float* __restrict__ istd, int training, BnGrads gr, float* __restrict__ k0, float* __restrict__ k1,
                        float* __restrict__ k2) {
+  pdl_prologue();
   __shared__ double sa[kBnSlices * kBnCh / 32][kBnCh], sb[kBnSlices * kBnCh / 32][kBnCh];
   const int cx = threadIdx.x & (kBnCh - 1), ry = threadIdx.x / kBnCh;
   const int ctot = G * C;
@@ -180,6 +185,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, int G, int C, doub
 // out[j*ostride] = sum_b rows[b*ld + j], j < n.  Block = 32 columns x 8 batch slices.
 __global__ void colsum_kernel(const float* __restrict__ rows, size_t ld, int B, int n, float* __restrict__ out,
                               int ostride) {
+  pdl_prologue();
   __shared__ float s[8][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
   float a = 0.f;
@@ -199,6 +205,7 @@ __global__ void colsum_kernel(const float* __restrict__ rows, size_t ld, int B, 
 // block, batch walked in shared-memory tiles of 32.
 __global__ void outer_sum_kernel(const float* __restrict__ U, size_t ldu, const float* __restrict__ V, size_t ldv,
                                  int B, int ni, int nj, float* __restrict__ out, size_t si, size_t sj) {
+  pdl_prologue();
   __shared__ float su[32][17];
   __shared__ float sv[32][17];
   const int tx = threadIdx.x, ty = threadIdx.y;  // 16 x 16
@@ -223,6 +230,7 @@ __global__ void outer_sum_kernel(const float* __restrict__ U, size_t ldu, const 
 // joint = s_spec * float(w) + s_spat * float(1-w),  w = sigmoid(alpha) in fp64 (Hang2020.py:259-260)
 __global__ void joint_fwd_kernel(const float* __restrict__ spec, const float* __restrict__ spat,
                                  const double* __restrict__ alpha, float* __restrict__ joint, size_t n) {
+  pdl_prologue();
   const double w = 1.0 / (1.0 + exp(-alpha[0]));
   const float wf = (float)w, vf = (float)(1.0 - w);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -233,6 +241,7 @@ __global__ void joint_fwd_kernel(const float* __restrict__ spec, const float* __
 __global__ void joint_bwd_kernel(const float* __restrict__ dspec, const float* __restrict__ dspat,
                                  const float* __restrict__ djoint, const double* __restrict__ alpha,
                                  float* __restrict__ out_spec, float* __restrict__ out_spat, size_t n) {
+  pdl_prologue();
   const double w = 1.0 / (1.0 + exp(-alpha[0]));
   const float wf = (float)w, vf = (float)(1.0 - w);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -246,6 +255,7 @@ __global__ void joint_bwd_kernel(const float* __restrict__ dspec, const float* _
 __global__ void alpha_grad_kernel(const float* __restrict__ djoint, const float* __restrict__ spec,
                                   const float* __restrict__ spat, const double* __restrict__ alpha, size_t n,
                                   double* __restrict__ dalpha) {
+  pdl_prologue();
   __shared__ double s[1024];
   double a = 0.0;
   for (size_t i = threadIdx.x; i < n; i += blockDim.x) a += (double)(djoint[i] * spec[i]) - (double)(djoint[i] * spat[i]);
@@ -286,6 +296,7 @@ struct ReduceTaskTable {
 
 // grid = (tiles, kReduceSplits); partial[tile][split][32*32]
 __global__ void __launch_bounds__(256) batched_reduce_kernel(const __grid_constant__ ReduceTaskTable tab, int B, float* __restrict__ partial) {
+  pdl_prologue();
   __shared__ float su[32][33];
   __shared__ float sv[32][33];
   int ti = 0;
@@ -341,6 +352,7 @@ __global__ void __launch_bounds__(256) batched_reduce_kernel(const __grid_consta
 
 // grid = tiles; sums the kReduceSplits partial tiles in fixed order and scatters to the gradient tensors.
 __global__ void __launch_bounds__(256) batched_reduce_finish_kernel(const __grid_constant__ ReduceTaskTable tab, const float* __restrict__ partial) {
+  pdl_prologue();
   int ti = 0;
   while (ti + 1 < tab.n && tab.t[ti + 1].tile_begin <= (int)blockIdx.x) ++ti;
   const ReduceTask& T = tab.t[ti];
@@ -370,6 +382,7 @@ __global__ void __launch_bounds__(256) batched_reduce_finish_kernel(const __grid
 }
 
 __global__ void fill_zero_kernel(float* __restrict__ p, size_t n) {
+  pdl_prologue();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 

@@ -13,6 +13,7 @@ constexpr int kPrepSlices = 4;   // band slices per pixel in the min/max pass
 // grid = crops, block = 128 pixels x kPrepSlices.  raw (B, C, HW) int16, out (B, C - 2*clip, HW) float32.
 __global__ void __launch_bounds__(128 * kPrepSlices)
 preprocess_crops_kernel(const short* __restrict__ raw, int C, int HW, int clip, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float s_min[kPrepSlices][128], s_max[kPrepSlices][128];
   const int p = threadIdx.x & 127, sl = threadIdx.x >> 7;
   const int b = blockIdx.x;

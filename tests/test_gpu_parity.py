@@ -224,19 +224,22 @@ def test_graphed_step_equals_eager_step():
 
 @pytest.mark.parametrize("kind,bands,classes,batch", [("hang2020", 369, 50, 48), ("spectral", 30, 7, 5), ("vanilla", 12, 4, 9)])
 def test_side_stream_overlap_is_bit_identical(kind, bands, classes, batch):
-    """Option "overlap" only moves launches to the library's side stream (fork/join with events): same kernels, same
-    arithmetic order, so scores, loss, gradients and BatchNorm buffers must be bit-identical with it on and off."""
+    """Options "overlap" (library side stream, fork/join with events) and "pdl" (programmatic dependent launch between
+    consecutive kernels) only change HOW launches are ordered, never the arithmetic: scores, loss, gradients and BatchNorm
+    buffers must be bit-identical for every combination."""
     from deeptreeattention_b200 import _capi
     table = orc.init_params(kind, bands, classes, 21, perturb_bn=True)
     x, y = orc.make_inputs(batch, bands, classes, 21)
     dev = torch.cuda.current_device()
     runs = []
     try:
-        for overlap in (1, 0, 1):
+        for overlap, pdl in ((1, 1), (0, 0), (1, 0), (0, 1), (1, 1)):
             _capi.set_option(dev, "overlap", overlap)
+            _capi.set_option(dev, "pdl", pdl)
             runs.append(run_cuda(kind, bands, classes, table, x, y, "R2" if kind != "vanilla" else "R1", True))
     finally:
         _capi.set_option(dev, "overlap", 1)
+        _capi.set_option(dev, "pdl", 1)
     for other in runs[1:]:
         assert other[0] == runs[0][0]
         assert np.array_equal(other[1], runs[0][1])
