@@ -800,15 +800,11 @@ int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, c
     h.ds[i] = dscores ? dscores[i] : nullptr;
   }
   double* den = static_cast<double*>(workspace);
-  int* bad = reinterpret_cast<int*>(static_cast<char*>(workspace) + 64);
   float* rows = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   StageScope sc(ctx, "loss.cross_entropy", st);
-  cudaMemsetAsync(bad, 0, sizeof(int), st);
-  launch_k(ce_den_kernel, 1, 256, 0, st, reinterpret_cast<const long long*>(labels), class_weight, batch, classes, den, bad);
-  DTA_CHECK_LAUNCH(ctx, "ce_den");
   const long long warps = (long long)n_heads * batch;
   launch_k(ce_rows_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, st, h, n_heads, reinterpret_cast<const long long*>(labels), class_weight, batch,
-                                                                     classes, den, rows);
+           classes, den, rows);
   DTA_CHECK_LAUNCH(ctx, "ce_rows");
   launch_k(ce_finish_kernel, 1, 256, 0, st, rows, n_heads, batch, den, loss);
   DTA_CHECK_LAUNCH(ctx, "ce_finish");

@@ -13,30 +13,30 @@ struct HeadPtrs {
   float* ds[8];
 };
 
-// den = sum_b w[y_b]  (fp64, fixed order; one block)
-__global__ void ce_den_kernel(const long long* __restrict__ y, const float* __restrict__ w, int B, int classes, double* __restrict__ den,
-                              int* __restrict__ bad_label) {
-  pdl_prologue();
-  __shared__ double s[256];
+// den = sum_b w[y_b] over the valid labels, computed by every CTA for itself (fp64, fixed order: every CTA gets the same
+// bits) instead of by a one-block kernel in front: one launch less on the step's critical path.
+__device__ __forceinline__ double ce_den_block(const long long* __restrict__ y, const float* __restrict__ w, int B, int classes, double* s_red) {
   double a = 0.0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const long long c = y[b];
-    if (c < 0 || c >= classes) { *bad_label = 1; continue; }
-    a += w ? (double)w[c] : 1.0;
+    if (c >= 0 && c < classes) a += w ? (double)__ldg(w + c) : 1.0;
   }
-  s[threadIdx.x] = a;
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) den[0] = s[0];
+  double t = 0.0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_red[i];
+  return t;
 }
 
-// One warp per (head, crop): stable log-softmax, weighted NLL term and the score gradient.
-__global__ void ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restrict__ y, const float* __restrict__ w, int B, int classes,
-                               const double* __restrict__ den, float* __restrict__ row_loss /*[n_heads][B]*/) {
+// One warp per (head, crop): stable log-softmax, weighted NLL term and the score gradient.  Block 0 also publishes den.
+__global__ void __launch_bounds__(256)
+ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restrict__ y, const float* __restrict__ w, int B, int classes,
+               double* __restrict__ den, float* __restrict__ row_loss /*[n_heads][B]*/) {
   pdl_prologue();
+  __shared__ double s_red[8];
+  const double dsum = ce_den_block(y, w, B, classes, s_red);
+  if (blockIdx.x == 0 && threadIdx.x == 0) den[0] = dsum;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= n_heads * B) return;
   const int head = gw / B, b = gw - head * B;
@@ -55,7 +55,7 @@ __global__ void ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restr
   if (lane == 0) row_loss[(size_t)head * B + b] = ok ? wy * (lse - __ldg(s + yc)) : 0.f;
   float* ds = h.ds[head];
   if (ds != nullptr) {
-    const float inv = (float)(1.0 / den[0]);
+    const float inv = (float)(1.0 / dsum);
     for (int c = lane; c < classes; c += 32) {
       const float p = expf(__ldg(s + c) - lse);
       ds[(size_t)b * classes + c] = wy * inv * (p - (c == yc ? 1.f : 0.f));
@@ -63,29 +63,29 @@ __global__ void ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restr
   }
 }
 
-// loss[head] = sum_b row_loss / den (fp64, fixed order), loss[n_heads] = sum over heads.  One block.
-__global__ void ce_finish_kernel(const float* __restrict__ row_loss, int n_heads, int B, const double* __restrict__ den, float* __restrict__ loss) {
+// loss[head] = sum_b row_loss / den (fp64, fixed order), loss[n_heads] = sum over heads.  One block, one warp per head.
+__global__ void __launch_bounds__(256)
+ce_finish_kernel(const float* __restrict__ row_loss, int n_heads, int B, const double* __restrict__ den, float* __restrict__ loss) {
   pdl_prologue();
-  __shared__ double s[256];
-  __shared__ double total;
-  if (threadIdx.x == 0) total = 0.0;
-  for (int head = 0; head < n_heads; ++head) {
+  __shared__ double s_head[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < n_heads) {
     double a = 0.0;
-    for (int b = threadIdx.x; b < B; b += blockDim.x) a += (double)row_loss[(size_t)head * B + b];
-    s[threadIdx.x] = a;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
-      __syncthreads();
+#pragma unroll 4
+    for (int b = lane; b < B; b += 32) a += (double)__ldg(row_loss + (size_t)warp * B + b);
+    a = warp_sum(a);
+    if (lane == 0) {
+      const double v = a / den[0];
+      loss[warp] = (float)v;
+      s_head[warp] = v;
     }
-    if (threadIdx.x == 0) {
-      const double v = s[0] / den[0];
-      loss[head] = (float)v;
-      total += v;
-    }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) loss[n_heads] = (float)total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double total = 0.0;
+    for (int hd = 0; hd < n_heads; ++hd) total += s_head[hd];
+    loss[n_heads] = (float)total;
+  }
 }
 
 }  // namespace dta
