@@ -366,10 +366,15 @@ class Hang2020(_FusedNet):
         self.spatial_network = spatial_network(bands, classes)
         self.alpha = nn.Parameter(torch.tensor(0.5, dtype=float), requires_grad=True)
 
+    @property
+    def weighted_average(self):
+        """sigmoid(alpha), the blend weight of the spectral branch (reference :260 stores it in forward; nothing in the
+        reference reads it back, so it is evaluated on access instead of costing a kernel launch every step)."""
+        return torch.sigmoid(self.alpha.detach())
+
     def forward(self, x):
         outs = self._fused(x)
         self.head_scores = list(outs[:6])        # spectral 1-3, spatial 1-3 (extra over the reference)
-        self.weighted_average = torch.sigmoid(self.alpha.detach())
         return outs[6]
 
 

@@ -701,10 +701,8 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
   if (shape->net_kind == DTA_NET_HANG2020) {
     StageScope sc(ctx, "fwd.joint", st);
     const size_t n = (size_t)B * classes;
-    launch_k(joint_fwd_kernel, (int)((n + 255) / 256), 256, 0, st, scores[2], scores[5], params->alpha, joint, n);
+    launch_k(joint_fwd_kernel, (int)((n + 255) / 256), 256, 0, st, scores[2], scores[5], params->alpha, joint, L.s3[0], L.s3[1], n);
     DTA_CHECK_LAUNCH(ctx, "joint_fwd");
-    cudaMemcpyAsync(L.s3[0], scores[2], n * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    cudaMemcpyAsync(L.s3[1], scores[5], n * sizeof(float), cudaMemcpyDeviceToDevice, st);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("forward: ") + cudaGetErrorString(e));
@@ -855,7 +853,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     DTA_CHECK_LAUNCH(ctx, "joint_bwd");
     dS[2] = W.dS[2]; dS[5] = W.dS[5];
     if (grads->alpha) {
-      launch_k(alpha_grad_kernel, 1, 1024, 0, st, djoint, L.s3[0], L.s3[1], params->alpha, nsc, grads->alpha);
+      launch_k(alpha_grad_kernel, 1, 1024, 0, ss, djoint, L.s3[0], L.s3[1], params->alpha, nsc, grads->alpha);   // off the critical path
       DTA_CHECK_LAUNCH(ctx, "alpha_grad");
     }
   } else if (hang && grads->alpha) {

@@ -97,6 +97,11 @@ bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int n
   __shared__ double ss[kBnSlices * kBnCh / 32][kBnCh], sq[kBnSlices * kBnCh / 32][kBnCh];
   const int cx = threadIdx.x & (kBnCh - 1), ry = threadIdx.x / kBnCh;
   const int ch = blockIdx.x * kBnCh + cx;
+  // the finishing threads fetch their channel's parameters up front: the loads travel under the partial-sum loop
+  const bool fin = ry == 0 && ch < ctot;
+  const int br = fin ? ch / bn.c_per_branch : 0, c = fin ? ch - br * bn.c_per_branch : 0;
+  float p_gamma = 0.f, p_beta = 0.f, p_rm = 0.f, p_rv = 1.f;
+  if (fin) { p_gamma = bn.gamma[br][c]; p_beta = bn.beta[br][c]; p_rm = bn.rm[br][c]; p_rv = bn.rv[br][c]; }
   double s = 0.0, q = 0.0;
   if (training && ch < ctot) {
 #pragma unroll 4
@@ -107,8 +112,7 @@ bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int n
     }
   }
   bn_block_sum2(s, q, ss, sq);
-  if (ry != 0 || ch >= ctot) return;
-  const int br = ch / bn.c_per_branch, c = ch - br * bn.c_per_branch;
+  if (!fin) return;
   float m, is;
   if (training) {
     const double mu = s / count;
@@ -117,18 +121,18 @@ bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int n
     m = (float)mu;
     is = (float)(1.0 / sqrt(var + (double)kBnEps));
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    bn.rm[br][c] = (float)((1.0 - kBnMomentum) * (double)bn.rm[br][c] + kBnMomentum * mu);
-    bn.rv[br][c] = (float)((1.0 - kBnMomentum) * (double)bn.rv[br][c] + kBnMomentum * unbiased);
+    bn.rm[br][c] = (float)((1.0 - kBnMomentum) * (double)p_rm + kBnMomentum * mu);
+    bn.rv[br][c] = (float)((1.0 - kBnMomentum) * (double)p_rv + kBnMomentum * unbiased);
     if (c == 0 && bn.nbt[br] != nullptr) bn.nbt[br][0] += 1;
   } else {
-    m = bn.rm[br][c];
-    is = (float)(1.0 / sqrt((double)bn.rv[br][c] + (double)kBnEps));
+    m = p_rm;
+    is = (float)(1.0 / sqrt((double)p_rv + (double)kBnEps));
   }
-  const float sc = bn.gamma[br][c] * is;
+  const float sc = p_gamma * is;
   mean[ch] = m;
   istd[ch] = is;
   scale[ch] = sc;
-  shift[ch] = bn.beta[br][c] - m * sc;
+  shift[ch] = p_beta - m * sc;
 }
 
 struct BnGrads {
@@ -151,6 +155,10 @@ bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, int G, int C, doub
   const int ctot = G * C;
   const int ch = blockIdx.x * kBnCh + cx;
   const int g = ch / C, c = ch - g * C;
+  const bool fin = ry == 0 && ch < ctot;
+  const int br = fin ? ch / bn.c_per_branch : 0, cb = fin ? ch - br * bn.c_per_branch : 0;
+  float p_gamma = 0.f, p_istd = 0.f, p_mean = 0.f;
+  if (fin) { p_gamma = bn.gamma[br][cb]; p_istd = istd[ch]; p_mean = mean[ch]; }
   double s1 = 0.0, s2 = 0.0;
   if (ch < ctot) {
 #pragma unroll 4
@@ -161,10 +169,9 @@ bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, int G, int C, doub
     }
   }
   bn_block_sum2(s1, s2, sa, sb);
-  if (ry != 0 || ch >= ctot) return;
-  const int br = ch / bn.c_per_branch, cb = ch - br * bn.c_per_branch;
-  const double gam = bn.gamma[br][cb];
-  const double is = istd[ch], mu = mean[ch];
+  if (!fin) return;
+  const double gam = p_gamma;
+  const double is = p_istd, mu = p_mean;
   const double a = gam * is;
   double b1 = 0.0, b2 = 0.0, dbias;
   if (training) {
@@ -229,12 +236,17 @@ __global__ void outer_sum_kernel(const float* __restrict__ U, size_t ldu, const 
 
 // joint = s_spec * float(w) + s_spat * float(1-w),  w = sigmoid(alpha) in fp64 (Hang2020.py:259-260)
 __global__ void joint_fwd_kernel(const float* __restrict__ spec, const float* __restrict__ spat,
-                                 const double* __restrict__ alpha, float* __restrict__ joint, size_t n) {
+                                 const double* __restrict__ alpha, float* __restrict__ joint, float* __restrict__ keep_spec,
+                                 float* __restrict__ keep_spat, size_t n) {
   pdl_prologue();
   const double w = 1.0 / (1.0 + exp(-alpha[0]));
   const float wf = (float)w, vf = (float)(1.0 - w);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    joint[i] = spec[i] * wf + spat[i] * vf;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float a = spec[i], b = spat[i];
+    joint[i] = a * wf + b * vf;
+    keep_spec[i] = a;   // copies of the two last-head scores for the alpha gradient (the caller owns `scores` and may reuse them)
+    keep_spat[i] = b;
+  }
 }
 
 // dS_spec = dscores_spec + djoint*w ; dS_spat = dscores_spat + djoint*(1-w)
