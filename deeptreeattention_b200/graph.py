@@ -19,10 +19,13 @@ class GraphedTrainStep:
     ``loss_fn(model, out, y)`` must be built from CUDA ops only (e.g. ``loss.cross_entropy_heads``).
     ``after_backward()`` (optional, e.g. ``GradSync.sync``) is captured too.  Gradients are left in
     ``p.grad`` exactly as an eager ``loss.backward()`` would leave them after ``p.grad = None``.
+    ``optimizer`` (optional): its ``step()`` is captured after the gradient exchange; it must keep its step counter and
+    learning rate on the device (``optim.FusedAdam(..., capturable=True)``).
     """
 
     def __init__(self, model: torch.nn.Module, x_example: torch.Tensor, y_example: torch.Tensor,
-                 loss_fn: Callable, after_backward: Optional[Callable[[], None]] = None, warmup: int = 3):
+                 loss_fn: Callable, after_backward: Optional[Callable[[], None]] = None, warmup: int = 3,
+                 optimizer: Optional[torch.optim.Optimizer] = None):
         if not x_example.is_cuda:
             raise RuntimeError("GraphedTrainStep needs CUDA tensors (no CPU path)")
         self.model = model
@@ -40,6 +43,8 @@ class GraphedTrainStep:
             loss.backward()
             if after_backward is not None:
                 after_backward()
+            if optimizer is not None:
+                optimizer.step()
             return loss
 
         # gradients are produced on the capture / warm-up stream while the AccumulateGrad nodes were created on the

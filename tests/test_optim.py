@@ -86,3 +86,36 @@ def test_fused_adam_trains_the_fused_model_and_reloads_state():
         if p in o1.state:
             assert torch.equal(o3.state[p]["exp_avg"], o1.state[p]["exp_avg"])
             assert int(o3.state[p]["step"]) == int(o1.state[p]["step"])
+
+
+@pytest.mark.gpu
+def test_graph_captured_step_with_fused_adam_matches_eager_torch_adam():
+    """forward + loss + backward + FusedAdam(capturable) replayed as ONE CUDA graph equals the eager loop with torch.optim.Adam."""
+    from deeptreeattention_b200 import Hang2020 as H
+    from deeptreeattention_b200.graph import GraphedTrainStep
+    from deeptreeattention_b200.loss import cross_entropy_heads
+    from deeptreeattention_b200.optim import FusedAdam
+    from oracle import hang2020_oracle as orc
+    table = orc.init_params("hang2020", 24, 5, 13)
+    x, y = orc.make_inputs(10, 24, 5, 13)
+    xd, yd = x.cuda(), y.cuda()
+    mg, me = H.Hang2020(24, 5), H.Hang2020(24, 5)
+    mg.load_state_dict(table), me.load_state_dict(table)
+    mg, me = mg.cuda().train(), me.cuda().train()
+
+    def loss_fn(m, out, yy):
+        return cross_entropy_heads(m.head_scores + [out], yy)
+
+    step = GraphedTrainStep(mg, xd, yd, loss_fn, warmup=1, optimizer=FusedAdam(mg.parameters(), lr=2e-3, capturable=True))
+    for _ in range(2):
+        loss_g = step(xd, yd)
+    opt = torch.optim.Adam(me.parameters(), lr=2e-3, foreach=False, fused=False)
+    for _ in range(3):                                   # 1 warm-up step + 2 replays
+        opt.zero_grad(set_to_none=True)
+        loss_e = loss_fn(me, me(xd), yd)
+        loss_e.backward()
+        opt.step()
+    torch.cuda.synchronize()
+    assert abs(float(loss_g) - float(loss_e)) < 1e-4
+    for (k, p), q in zip(mg.named_parameters(), me.parameters()):
+        assert float((p.detach().double() - q.detach().double()).abs().max()) <= 2e-5 + 2e-5 * float(q.detach().abs().max()), k

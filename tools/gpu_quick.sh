@@ -7,6 +7,6 @@ timeout 240 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_b
 python - <<PY
 import json
 d = json.load(open("gpurun_out/${TAG}_bench.json"))
-print(round(d["value"]), "crops/s", round(d["ms_per_step"], 4), "ms e2e", round(d["e2e"]["value"]), "adam_ms", d.get("with_adam", {}).get("adam_ms_per_step"))
+print(round(d["value"]), "crops/s", round(d["ms_per_step"], 4), "ms e2e", round(d["e2e"]["value"]), "with_adam", (d.get("with_adam") or {}).get("value"))
 print(d["roofline"]["stages_ms_per_step"])
 PY

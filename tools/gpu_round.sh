@@ -15,7 +15,7 @@ import json
 for n in ("bench", "bench_nooverlap", "bench_eager"):
     try:
         d = json.load(open("gpurun_out/${TAG}_%s.json" % n))
-        print(n, round(d["value"]), "crops/s", round(d["ms_per_step"], 4), "ms e2e", round(d["e2e"]["value"]), "adam_ms", d.get("with_adam", {}).get("adam_ms_per_step"))
+        print(n, round(d["value"]), "crops/s", round(d["ms_per_step"], 4), "ms e2e", round(d["e2e"]["value"]), "with_adam", (d.get("with_adam") or {}).get("value"))
     except Exception as e:
         print(n, "unreadable", e)
 PY
