@@ -166,3 +166,22 @@ def test_blocks_compose_like_the_fused_network():
     head.fc1 = net.fc1
     composed = head(torch.flatten(h, start_dim=1))
     np.testing.assert_allclose(composed.detach().cpu().numpy(), fused.detach().cpu().numpy(), rtol=0, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_block_argument_errors():
+    from deeptreeattention_b200 import Hang2020 as H
+    with pytest.raises(ValueError):
+        H.conv_module(in_channels=8, filters=4).cuda()(torch.randn(2, 7, 11, 11).cuda())        # channel mismatch
+    with pytest.raises(AttributeError):
+        H.conv_module(in_channels=8, filters=4).cuda()(torch.randn(2, 8, 11, 11).cuda(), pool=True)   # no max_pool, like the reference
+    with pytest.raises(ValueError):
+        H.spatial_attention(filters=64).cuda()(torch.randn(2, 32, 5, 5).cuda())
+    with pytest.raises(TypeError):
+        H.spectral_attention(filters=32).cuda()(torch.randn(2, 32, 5, 5).cuda().double())
+    with pytest.raises(ValueError):
+        H.Classifier(in_features=16, classes=3).cuda()(torch.randn(2, 8).cuda())
+    # a plane larger than the crops of the networks works too (generic kernels)
+    m = H.spatial_attention(filters=32).cuda()
+    out, feat = m(torch.randn(2, 32, 16, 13).cuda())
+    assert out.shape == (2, 32, 16, 13) and feat.shape == (2, 32 * 4 * 3)

@@ -39,6 +39,32 @@ def test_query_sizes_and_bad_shapes():
         _capi.query_sizes(_capi.NET_HANG2020, 0, 3, 2, True)
 
 
+def test_host_side_size_queries_of_blocks_and_pairs():
+    """Pure host arithmetic of the newer entry points (no GPU needed): block workspaces, attention geometry, pair kinds."""
+    import ctypes as C
+    from deeptreeattention_b200 import _capi
+    L = _capi.lib()
+    plane = _capi.Plane(20, 369, 11, 11)
+    need = C.c_size_t()
+    assert L.dta_conv_module_workspace_bytes(C.byref(plane), 32, C.byref(need)) == 0
+    assert need.value == (20 * 32 * 121 + 3 * 32) * 4
+    assert L.dta_conv_module_workspace_bytes(C.byref(plane), 0, C.byref(need)) == -1
+    feat, saved, work = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    for kind, filters, side, nfeat, nsaved in ((_capi.ATTN_SPECTRAL, 32, 11, 32, 96), (_capi.ATTN_SPECTRAL, 128, 2, 128, 384),
+                                               (_capi.ATTN_SPATIAL, 32, 11, 128, 363), (_capi.ATTN_SPATIAL, 64, 5, 256, 75),
+                                               (_capi.ATTN_SPATIAL, 128, 2, 512, 12)):
+        pl = _capi.Plane(20, filters, side, side)
+        assert L.dta_attention_sizes(kind, C.byref(pl), C.byref(feat), C.byref(saved), C.byref(work)) == 0
+        assert (feat.value, saved.value) == (nfeat, nsaved) and work.value > 0
+    bad = _capi.Plane(20, 48, 11, 11)                      # reference: ValueError for filters outside {32, 64, 128}
+    assert L.dta_attention_sizes(_capi.ATTN_SPATIAL, C.byref(bad), C.byref(feat), C.byref(saved), C.byref(work)) == -2
+    pair = _capi.query_sizes(_capi.NET_SPECTRAL_PAIR, 64, 369, 9, False)
+    single = _capi.query_sizes(_capi.NET_SPECTRAL, 64, 369, 9, False)
+    assert pair.n_heads == 6 and single.n_heads == 3 and pair.saved_bytes > single.saved_bytes
+    hyper = _capi.AdamHyper(1e-3, 0.9, 0.999, 1e-8, 0.0, 1)
+    assert L.dta_adam_step(None, 0, None, None, None, None, None, None, None, None, None, C.byref(hyper), None, None, None) == -1
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_create_fails_loudly_without_gpu():
     from deeptreeattention_b200 import _capi
