@@ -62,8 +62,8 @@ struct Carver {
 // Tensor-core path geometry.  Two position streams: side 11 (conv1, conv2 and their gradients) and
 // side 5 (conv3).  Buffers are padded so that every kernel's tile size divides the stream length.
 using WgradCfg1 = TcWgrad<128, 128, true, 3, 2>;  // conv1: merged 64 output channels (hi/lo stacked), 128-channel slices, 3 tap groups
-using WgradCfg2 = TcWgrad<32, 128, true>;    // conv2: 64 output channels per branch, 32 input channels
-using WgradCfg3 = TcWgrad<32, 64, false>;    // conv3: 128 output channels per branch, 2 slices of 32 input channels
+using WgradCfg2 = TcWgrad<32, 128, true, 1, 2>;    // conv2: 64 output channels per branch, 32 input channels
+using WgradCfg3 = TcWgrad<32, 64, false, 1, 2>;    // conv3: 128 output channels per branch, 2 slices of 32 input channels
 constexpr int kTcSmCount = 148;              // split-K factors are sized for the B200's 148 SMs (dta_query_sizes has no device)
 
 struct TcSplit { int nkstage, nslices, nsplit, per; };
