@@ -118,12 +118,19 @@ def lib():
     with _lock:
         if _lib is not None:
             return _lib
-        if needs_build():
-            if os.path.exists(LIB_PATH) and not (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
-                pass  # prebuilt binary on a box without nvcc: use it
-            else:
-                build()
-        L = C.CDLL(LIB_PATH)
+        override = os.environ.get("DTA_B200_LIB")      # a prebuilt libdta_b200.so to load instead (A/B runs of kernel variants)
+        if override:
+            if not os.path.exists(override):
+                raise RuntimeError(f"DTA_B200_LIB={override} does not exist")
+            path = override
+        else:
+            if needs_build():
+                if os.path.exists(LIB_PATH) and not (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+                    pass  # prebuilt binary on a box without nvcc: use it
+                else:
+                    build()
+            path = LIB_PATH
+        L = C.CDLL(path)
         L.dta_abi_version.restype = C.c_int
         L.dta_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
         L.dta_create.restype = C.c_int
