@@ -471,7 +471,7 @@ def run_b200(args):
         "config": {"workload": f"Hang2020(bands={bands}, classes={classes}) fwd+CE({args.regime})+bwd"
                                + ("+grad all-reduce" if world > 1 else "") + f", {B} crops per GPU per step",
                    "regime": args.regime, "launch": "cuda-graph replay" if args.graph else "eager", "batch_per_gpu": B, "global_batch": B * world,
-                   "side_stream_overlap": bool(args.overlap), "programmatic_dependent_launch": bool(args.pdl), "parallelism": f"dp{world}", "gradient_exchange": sync.last_path if world > 1 else None, "l2": f"crops per step = {B * bands * 484 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
+                   "side_stream_overlap": int(args.overlap), "programmatic_dependent_launch": bool(args.pdl), "parallelism": f"dp{world}", "gradient_exchange": sync.last_path if world > 1 else None, "l2": f"crops per step = {B * bands * 484 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
                    if B * bands * 484 > 126e6 else "flush: none (inputs smaller than L2)"},
         "roofline": roof, "cpu_baseline": cpu, "clocks": clock_rec,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_dev.numel() * 4, "d2h_bytes_per_step": 4,
@@ -501,7 +501,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")
     ap.add_argument("--pdl", type=int, default=1, help="library option \"pdl\": 1 = programmatic dependent launch between kernels (default)")
-    ap.add_argument("--overlap", type=int, default=1, help="library option \"overlap\": 1 = side-stream overlap of off-critical-path work (default)")
+    ap.add_argument("--overlap", type=int, default=2,
+                    help="library option \"overlap\": 0 = caller's stream only, 1 = one side stream, 2 = + auxiliary stream (default)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -419,6 +419,7 @@ int dta_create(dta_ctx** out, int device) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi) != cudaSuccess) c->side = nullptr;
+    if (cudaStreamCreateWithPriority(&c->aux, cudaStreamNonBlocking, hi) != cudaSuccess) c->aux = nullptr;
     for (int i = 0; i < 32 && c->side; ++i) {
       cudaEvent_t e = nullptr;
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) c->sync_events.push_back(e);
@@ -436,6 +437,7 @@ void dta_destroy(dta_ctx* ctx) {
   for (cudaEvent_t e : ctx->free_events) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->sync_events) cudaEventDestroy(e);
   if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
   delete ctx;
 }
 
@@ -474,7 +476,8 @@ int dta_set_option(dta_ctx* ctx, const char* key, int64_t value) {
     return DTA_OK;
   }
   if (!strcmp(key, "overlap")) {
-    ctx->overlap = value != 0;
+    if (value < 0 || value > 2) return fail(ctx, DTA_ERR_INVALID_ARG, "overlap must be 0, 1 or 2");
+    ctx->overlap = (int)value;
     return DTA_OK;
   }
   if (!strcmp(key, "pdl")) {
@@ -841,6 +844,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   // parameter packing and gradient zero-fill first, then each block's weight gradient (+ split-K reduce) under the NEXT
   // block's attention backward, the batched small-parameter reduction under conv1's weight gradient.
   SideStream side(ctx, st);
+  SideStream aux(ctx, st, 1);
   side.wait_main();
   cudaStream_t ss = side.stream();
 
@@ -1080,12 +1084,15 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     // every attention block has left its per-crop partials: ONE batched reduction for all small parameter gradients, on the
     // side stream (under BatchNorm backward / pack / conv1's weight gradient)
     if (rtiles > 0) {
-      side.wait_main();
-      StageScope sc(ctx, "bwd.small_param_grads", ss);
+      // on the auxiliary stream when there is one: queued behind conv2's weight gradient it would hold back conv1's, the
+      // last kernel of the step (the gradient zero-fill it depends on was joined into the caller's stream in block 3)
+      cudaStream_t rs = aux.on ? aux.stream() : ss;
+      if (aux.on) aux.wait_main(); else side.wait_main();
+      StageScope sc(ctx, "bwd.small_param_grads", rs);
       if (rtiles > reduce_tiles_bound(classes, nb)) return fail(ctx, DTA_ERR_UNSUPPORTED, "reduction tile bound exceeded");
-      launch_k(batched_reduce_kernel, dim3(rtiles, kReduceSplits), 256, 0, ss, rtab, B, W.rpart);
+      launch_k(batched_reduce_kernel, dim3(rtiles, kReduceSplits), 256, 0, rs, rtab, B, W.rpart);
       DTA_CHECK_LAUNCH(ctx, "batched_reduce");
-      launch_k(batched_reduce_finish_kernel, rtiles, 256, 0, ss, rtab, W.rpart);
+      launch_k(batched_reduce_finish_kernel, rtiles, 256, 0, rs, rtab, W.rpart);
       DTA_CHECK_LAUNCH(ctx, "batched_reduce_finish");
     }
     if ((rc = bn_bwd(0)) != DTA_OK) return rc;
@@ -1110,6 +1117,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     if (dx) return fail(ctx, DTA_ERR_UNSUPPORTED, "gradient of the crops (dx) is not built yet; the reference feeds requires_grad=False inputs");
   }
   side.join();
+  aux.join();
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("backward: ") + cudaGetErrorString(e));
   return DTA_OK;

@@ -30,9 +30,10 @@ struct dta_ctx {
   std::string err;
   // Side stream for work off the critical path (parameter packing, weight gradients): forked from / joined to the caller's
   // stream with the events below, so the caller still sees one stream-ordered call (and a CUDA-graph capture sees a DAG).
-  int overlap = 1;
+  int overlap = 2;     // 0: caller's stream only; 1: one side stream; 2: + auxiliary stream for the small-parameter reduction
   int pdl = 1;         // programmatic dependent launch between consecutive kernels (launch_k below)
   cudaStream_t side = nullptr;
+  cudaStream_t aux = nullptr;   // second side stream (option "overlap" = 2): work that must not queue behind the weight gradients
   std::vector<cudaEvent_t> sync_events;
   size_t sync_next = 0;
 };
@@ -126,10 +127,14 @@ inline cudaError_t launch_k(void (*kernel)(P...), dim3 grid, dim3 block, size_t 
 struct SideStream {
   dta_ctx* ctx;
   cudaStream_t main;
+  cudaStream_t side;
   bool on;
   bool pending = false;   // side work enqueued since the last join
-  SideStream(dta_ctx* c, cudaStream_t m) : ctx(c), main(m), on(c->overlap != 0 && c->profile == 0 && c->side != nullptr && !c->sync_events.empty()) {}
-  cudaStream_t stream() const { return on ? ctx->side : main; }
+  // which = 0: the weight-gradient side stream; which = 1: the auxiliary side stream (active from "overlap" = 2)
+  SideStream(dta_ctx* c, cudaStream_t m, int which = 0)
+      : ctx(c), main(m), side(which == 0 ? c->side : c->aux),
+        on(c->overlap > which && c->profile == 0 && (which == 0 ? c->side : c->aux) != nullptr && !c->sync_events.empty()) {}
+  cudaStream_t stream() const { return on ? side : main; }
   cudaEvent_t next_event() {
     cudaEvent_t e = ctx->sync_events[ctx->sync_next];
     ctx->sync_next = (ctx->sync_next + 1) % ctx->sync_events.size();
@@ -140,14 +145,14 @@ struct SideStream {
     if (!on) return;
     cudaEvent_t e = next_event();
     cudaEventRecord(e, main);
-    cudaStreamWaitEvent(ctx->side, e, 0);
+    cudaStreamWaitEvent(side, e, 0);
     pending = true;
   }
   // the caller's stream waits for everything enqueued on the side stream so far
   void join() {
     if (!on || !pending) return;
     cudaEvent_t e = next_event();
-    cudaEventRecord(e, ctx->side);
+    cudaEventRecord(e, side);
     cudaStreamWaitEvent(main, e, 0);
     pending = false;
   }

@@ -123,9 +123,10 @@ const char* dta_last_error(const dta_ctx* ctx); /* ctx may be NULL: last create 
  * 1 = tcgen05 split-bf16 implicit GEMM (default where implemented).
  * key "launches": read-only counter of kernels launched by the last forward/backward.
  * key "profile": 1 = record per-stage CUDA-event timings (see dta_profile_read).
- * key "overlap": 1 (default) = work off the critical path (parameter packing, weight gradients, small reductions) runs on a
+ * key "overlap": 2 (default) / 1 = work off the critical path (parameter packing, weight gradients, small reductions) runs on a
  * library-owned side stream, forked from and joined back to the caller's stream with events inside each call (still one
- * stream-ordered call for the caller; a CUDA-graph capture records a DAG); 0 = everything on the caller's stream.
+ * stream-ordered call for the caller; a CUDA-graph capture records a DAG); 2 adds a second side stream so that the batched
+ * small-parameter reduction does not queue between two weight gradients; 0 = everything on the caller's stream.
  * key "pdl": 1 (default) = consecutive kernels of a call are launched with programmatic dependent launch (the next kernel's
  * CTAs are scheduled while the previous grid drains and wait for its completion before touching memory): same stream order,
  * less launch latency between the ~60 short kernels of a step; 0 = plain launches. */

@@ -233,12 +233,12 @@ def test_side_stream_overlap_is_bit_identical(kind, bands, classes, batch):
     dev = torch.cuda.current_device()
     runs = []
     try:
-        for overlap, pdl in ((1, 1), (0, 0), (1, 0), (0, 1), (1, 1)):
+        for overlap, pdl in ((2, 1), (0, 0), (1, 0), (0, 1), (2, 0), (1, 1), (2, 1)):
             _capi.set_option(dev, "overlap", overlap)
             _capi.set_option(dev, "pdl", pdl)
             runs.append(run_cuda(kind, bands, classes, table, x, y, "R2" if kind != "vanilla" else "R1", True))
     finally:
-        _capi.set_option(dev, "overlap", 1)
+        _capi.set_option(dev, "overlap", 2)
         _capi.set_option(dev, "pdl", 1)
     for other in runs[1:]:
         assert other[0] == runs[0][0]
