@@ -398,7 +398,7 @@ def run_b200(args):
     #      gradient exchange (src/main.py:135-136), device-timed like `value` ------------------------------------------------
     from deeptreeattention_b200.optim import FusedAdam
     adam_ms = None
-    if args.graph:
+    if args.graph and world == 1:       # N = 1 only: a second captured graph holding the peer all-reduce has not been validated
         opt = FusedAdam(model.parameters(), lr=1e-4, capturable=True)
         graphed_opt = GraphedTrainStep(model, x_dev, y_dev,
                                        lambda m, out, y: cross_entropy_heads([out] if args.regime == "R1" else m.head_scores, y),
