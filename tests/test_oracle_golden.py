@@ -26,6 +26,24 @@ def test_oracle_matches_reference_golden(case):
     gu.check_grads(gold, grads, rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("case", gu.cases(), ids=lambda c: c["name"])
+def test_numpy_oracle_matches_reference_golden(case):
+    """The independent numpy float64 restatement of the forward pass (oracle/numpy_oracle.py: no ATen kernels) reproduces the
+    reference's scores and BatchNorm running statistics: 2e-5 abs (the goldens are float32 evaluations)."""
+    from oracle import numpy_oracle as npo
+    gold = gu.load(case)
+    table, x, _ = gu.build(case)
+    result, heads, bufs = npo.forward(case["kind"], table, x, case["training"])
+    np.testing.assert_allclose(result, gold["result"], rtol=0, atol=2e-5)
+    for i, h in enumerate(heads):
+        np.testing.assert_allclose(h, gold[f"head{i}"], rtol=0, atol=2e-5)
+        top2 = np.sort(gold[f"head{i}"], axis=1)[:, -2:]
+        safe = (top2[:, 1] - top2[:, 0]) > 1e-4
+        assert np.array_equal(h.argmax(1)[safe], gold[f"head{i}"].argmax(1)[safe])
+    for k, v in bufs.items():
+        np.testing.assert_allclose(v, gold[f"buf/{k}"], rtol=1e-5, atol=1e-6)
+
+
 def test_param_table_matches_appendix_d():
     names = [n for n, _, _ in orc.param_shapes("hang2020", 369, 50)]
     assert len(names) == 85 and names[0] == "alpha"
