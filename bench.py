@@ -213,6 +213,54 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_torch_eager(args):
+    """--impl torch_eager: the incumbent GPU path -- the reference's layer stack (oracle port: the same ATen ops
+    the reference's torch.nn modules dispatch, cuDNN / cuBLAS kernels) through stock PyTorch eager on cuda:0, with cuDNN TF32
+    convolutions on (PyTorch's default) and off.  Prints {"tf32": crops/s, "fp32": crops/s}; run by the b200 arm in a
+    subprocess so that nothing it does can disturb the headline measurement."""
+    from oracle import hang2020_oracle as orc
+    dev = torch.device(os.environ.get("DTA_BENCH_TORCH_DEVICE", "cuda:0"))
+    m = orc.OracleModule("hang2020", args.bands, args.classes, seed=0).to(dev).train()
+    x, y = synth_batch(args.batch, args.bands, args.classes, 0)
+    x, y = x.to(dev), y.to(dev)
+    out = {}
+    for name, tf32 in (("tf32", True), ("fp32", False)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        times = []
+        for i in range(args.warmup + args.steps):
+            for p in m.parameters():
+                p.grad = None
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            joint = m(x)
+            loss_of(args.regime, joint, m.heads, y).backward()
+            if dev.type == "cuda":
+                torch.cuda.synchronize()
+            if i >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        out[name] = args.batch * len(times) / sum(times)
+    print(json.dumps(out), flush=True)
+
+
+def torch_eager_gpu_baseline(args):
+    """Runs run_torch_eager in a child process (bounded by a timeout) and returns its dict, or why it is unavailable."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "torch_eager", "--steps", "10", "--warmup", "3", "--batch", str(args.batch),
+           "--bands", str(args.bands), "--classes", str(args.classes), "--regime", args.regime]
+    try:
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
+        lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode != 0 or not lines:
+            return {"unavailable": (res.stderr.strip().splitlines() or ["no output"])[-1][:200]}
+        d = json.loads(lines[-1])
+        return {"value_tf32": d["tf32"], "value_fp32": d["fp32"], "unit": UNIT,
+                "how": f"extra: the reference's layer stack (oracle port, ATen/cuDNN kernels) through stock PyTorch {torch.__version__} eager "
+                       "on the same GPU, 10 timed steps after 3 warm-up, cuDNN TF32 convolutions on (PyTorch default) / off"}
+    except Exception as e:  # noqa: BLE001  (a baseline that cannot run must not take the benchmark down)
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 # ----------------------------------------------------------------------------- this repo's arm
 def run_b200(args):
     import torch.distributed as dist
@@ -464,6 +512,8 @@ def run_b200(args):
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"2 timed steps x {cb} crops (1 warm-up) of the same workload, oracle port on torch {torch.__version__} CPU ATen, {cores} threads"}
 
+    torch_gpu = torch_eager_gpu_baseline(args) if (world == 1 and not args.no_cpu) else None
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -473,7 +523,7 @@ def run_b200(args):
                    "regime": args.regime, "launch": "cuda-graph replay" if args.graph else "eager", "batch_per_gpu": B, "global_batch": B * world,
                    "side_stream_overlap": int(args.overlap), "programmatic_dependent_launch": bool(args.pdl), "parallelism": f"dp{world}", "gradient_exchange": sync.last_path if world > 1 else None, "l2": f"crops per step = {B * bands * 484 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
                    if B * bands * 484 > 126e6 else "flush: none (inputs smaller than L2)"},
-        "roofline": roof, "cpu_baseline": cpu, "clocks": clock_rec,
+        "roofline": roof, "cpu_baseline": cpu, "torch_eager_gpu_baseline": torch_gpu, "clocks": clock_rec,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_dev.numel() * 4, "d2h_bytes_per_step": 4,
                 "how": "pinned host crops -> double-buffered H2D on a copy stream -> model(x) -> CE -> backward -> loss.item()"},
         "e2e_raw_int16": {"value": e2e_raw_value, "unit": UNIT, "h2d_bytes_per_step": raw_buf[0].numel() * 2, "d2h_bytes_per_step": 4,
@@ -493,7 +543,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_eager"])
     ap.add_argument("--batch", type=int, default=1024, help="crops per GPU per step")
     ap.add_argument("--bands", type=int, default=369)
     ap.add_argument("--classes", type=int, default=50)
@@ -506,6 +556,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_eager":
+        run_torch_eager(args)
     else:
         run_b200(args)
 
