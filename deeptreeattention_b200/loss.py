@@ -2,7 +2,7 @@
 
 ``cross_entropy_heads([s1, ..., sk], y, weight)`` equals ``sum(F.cross_entropy(s, y, weight=weight) for s in heads)``
 -- with one head it is exactly the reference's ``TreeModel.training_step`` loss
-(/root/reference/src/main.py:78) -- but runs as three kernel launches that also leave the score
+(/root/reference/src/main.py:78) -- but runs as two kernel launches that also leave the score
 gradients behind, so ``backward()`` launches nothing for the loss.
 """
 from __future__ import annotations
