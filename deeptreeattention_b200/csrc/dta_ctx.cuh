@@ -18,7 +18,7 @@ struct ProfSpan {
 struct dta_ctx {
   int device = 0;
   int sm_count = 0;
-  int conv_impl = 1;   // 1: tcgen05 split-bf16 implicit GEMM where built (conv1 forward + weight gradient), 0: fp32 SIMT
+  int conv_impl = 1;   // 1: tcgen05 split-bf16 implicit GEMM (every convolution, forward / input gradient / weight gradient), 0: fp32 SIMT
   long long launches = 0;
   int profile = 0;
   int fuse_x = 1;      // conv1 forward converts the raw crops itself (no separate pack pass); 0 = pack kernel + pre-packed operand

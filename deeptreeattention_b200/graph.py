@@ -1,6 +1,7 @@
 """CUDA-graph capture of one training step (forward + loss + backward [+ gradient all-reduce]).
 
-The hot path is ~45 kernel launches of a few tens of microseconds each; replaying them as one CUDA graph
+The hot path is ~60 kernel launches of a few tens of microseconds each on up to three streams (the library forks its
+side streams with events, which a capture records as a DAG); replaying them as one CUDA graph
 removes the host launch overhead and the gaps between kernels.  The library only *enqueues* work on the
 current stream and takes every buffer from the caller (torch's caching allocator), so a step is capturable
 as is: buffers allocated during capture live in the graph's private pool and keep their addresses, which
