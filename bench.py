@@ -497,7 +497,9 @@ def run_b200(args):
     if os.path.exists(traffic_file):
         with open(traffic_file) as f:
             t = json.load(f)
-        if t.get("kernel") == dominant:
+        if dominant in t.get("kernels", {}):
+            roof["traffic"] = t["kernels"][dominant].get("dram_bytes_per_launch")
+        elif t.get("kernel") == dominant:
             roof["traffic"] = t.get("dram_bytes_per_launch")
 
     # ---- CPU baseline (bounded sample, rank 0, N = 1 only) ------------------------------------
