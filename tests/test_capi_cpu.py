@@ -145,3 +145,23 @@ def test_year_and_metadata_modules_mirror_the_reference_surface():
     assert M.metadata(sites=1, classes=10)(torch.zeros(20).int()).shape == (20, 10)     # tests/test_metadata.py:11-15 (pure torch MLP)
     with pytest.raises(RuntimeError):
         f(torch.randn(2, 3, 11, 11), torch.zeros(2).int())
+
+
+def test_product_code_never_touches_the_oracle_or_a_cpu_fallback():
+    """The oracle is test infrastructure: nothing under deeptreeattention_b200/ may import it, and no product module may
+    import the reference tree either."""
+    import ast
+    import os
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deeptreeattention_b200")
+    for name in sorted(os.listdir(root)):
+        if not name.endswith(".py"):
+            continue
+        tree = ast.parse(open(os.path.join(root, name)).read())
+        for node in ast.walk(tree):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            for m in mods:
+                assert not m.split(".")[0] in ("oracle", "src"), f"{name} imports {m}"
