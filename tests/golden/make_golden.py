@@ -19,6 +19,12 @@ stable (5e-4 relative) under three random 3e-6 relative perturbations of crops a
 is recorded in cases.json and the measured per-tensor sensitivity is stored next to each
 gradient (``grad/<name>/sens``) so tests can widen the tolerance by the reference's own
 conditioning instead of guessing.
+
+Live-gate screening.  A spatial attention block whose 1x1 channel pool is negative for every
+pixel of every crop sits behind a dead ReLU (``Hang2020.py:108-109``): its ``channel_pool`` /
+stencil gradients are identically zero and the block's backward is never exercised.  With the
+default initialisation that happens for about half of all (seed, block) pairs, so seeds are also
+advanced until every ``channel_pool.weight`` gradient of the case is non-zero.
 """
 import importlib.util
 import os
@@ -71,6 +77,9 @@ def kink_stable(ref, case, seed, eps=3e-6, tol=5e-4, draws=3):
     table = orc.init_params(kind, bands, classes, seed, perturb_bn=perturb)
     x, y = orc.make_inputs(batch, bands, classes, seed, dist)
     base = orc.step(kind, table, x, y, regime=regime, training=training)[3]
+    for k, g in base.items():      # live-gate screening: every spatial gate must pass gradient
+        if k.endswith("channel_pool.weight") and g is not None and float(g.abs().max()) == 0.0:
+            return False, {}
     gen = torch.Generator().manual_seed(seed)
     sens = {k: 0.0 for k, g in base.items() if g is not None}
     stable = True
