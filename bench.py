@@ -159,20 +159,45 @@ def loss_of(regime, joint, heads, y):
     return sum(F.cross_entropy(h, y) for h in heads)
 
 
-def cpu_reference_rate(bands, classes, batch, regime, steps, warmup, threads):
-    """The reference's algorithm (oracle port: the same ATen CPU ops the reference's torch.nn
-    layers dispatch) for `steps` timed steps of `batch` crops on `threads` host threads."""
+def workload_string(args, world):
+    """One description of the workload for both arms (the reference arm runs a bounded per-step sample of it)."""
+    return (f"Hang2020(bands={args.bands}, classes={args.classes}) fwd+CE({args.regime})+bwd"
+            + ("+grad all-reduce" if world > 1 else "") + f", {args.batch} crops per GPU per step")
+
+
+def reference_module(bands, classes):
+    """(module, kind): the reference's OWN ``src/models/Hang2020.py`` (``kind = "reference"``: read from /root/reference in
+    the build container, from the unmodified copy under oracle/_ref on the GPU box -- oracle/ref_loader.py), else the oracle
+    port (``kind = "port"``: the same ATen CPU ops, pinned to the reference's outputs by tests/golden)."""
+    from oracle import ref_loader
+    ref = ref_loader.load("Hang2020")
+    torch.manual_seed(0)
+    if ref is not None:
+        return ref.Hang2020(bands, classes).train(), "reference"
     from oracle import hang2020_oracle as orc
+    return orc.OracleModule("hang2020", bands, classes, seed=0).train(), "port"
+
+
+def cpu_reference_rate(bands, classes, batch, regime, steps, warmup, threads, model=None):
+    """The reference's CPU implementation of the step for `steps` timed steps of `batch` crops on `threads` host threads.
+    R1: ``CE(Hang2020.forward(x))`` (src/main.py:77-78); R2: CE summed over the six heads, obtained on the reference module
+    the way SURVEY.md 0.3 prescribes: ``m.spectral_network(x) + m.spatial_network(x)`` (the two calls Hang2020.forward makes)."""
     torch.set_num_threads(threads)
-    m = orc.OracleModule("hang2020", bands, classes, seed=0).train()
+    m, kind = model if model is not None else reference_module(bands, classes)
     x, y = synth_batch(batch, bands, classes, 0)
     times = []
     for i in range(warmup + steps):
         for p in m.parameters():
             p.grad = None
         t0 = time.perf_counter()
-        joint = m(x)
-        loss = loss_of(regime, joint, m.heads, y)
+        if kind == "reference":
+            if regime == "R1":
+                loss = F.cross_entropy(m(x), y)
+            else:
+                loss = sum(F.cross_entropy(h, y) for h in m.spectral_network(x) + m.spatial_network(x))
+        else:
+            joint = m(x)
+            loss = loss_of(regime, joint, m.heads, y)
         loss.backward()
         t1 = time.perf_counter()
         if i >= warmup:
@@ -182,31 +207,33 @@ def cpu_reference_rate(bands, classes, batch, regime, steps, warmup, threads):
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU path (kind "port": /root/reference is Python
-    and cannot travel to the GPU box; the oracle restates it over the same ATen kernels and is
-    pinned to the reference's outputs by tests/golden)."""
+    """--impl reference: the reference's own module on the box's host cores (kind "reference" when its three torch-only model
+    files were copied to oracle/_ref by __graft_entry__.build(); kind "port" = the oracle restatement otherwise)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     threads = cores
     batch = args.batch
+    model = reference_module(args.bands, args.classes)
+    kind = model[1]
     # bound the run: calibrate on a small sample, shrink the per-step sample until the whole
     # --steps/--warmup run fits in ~150 s
-    rate0, _ = cpu_reference_rate(args.bands, args.classes, 64, args.regime, 1, 1, threads)
+    rate0, _ = cpu_reference_rate(args.bands, args.classes, 64, args.regime, 1, 1, threads, model)
     budget = 150.0
     while batch > 64 and (args.steps + args.warmup) * batch / rate0 > budget:
         batch //= 2
-    rate, sec = cpu_reference_rate(args.bands, args.classes, batch, args.regime, args.steps, args.warmup, threads)
+    rate, sec = cpu_reference_rate(args.bands, args.classes, batch, args.regime, args.steps, args.warmup, threads, model)
+    what = ("weecology/DeepTreeAttention src/models/Hang2020.py (unmodified)" if kind == "reference" else "oracle port")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Hang2020(bands={args.bands}, classes={args.classes}) fwd+CE({args.regime})+bwd, "
-                               f"{batch} crops per step on host cores", "regime": args.regime},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps x {batch} crops after {args.warmup} warm-up, torch {torch.__version__} "
-                                   f"CPU ATen (oneDNN) on {threads} threads of {cores} cores"},
+        "config": {"workload": workload_string(args, args.gpus), "regime": args.regime, "batch_per_gpu": args.batch,
+                   "sample_crops_per_step": batch, "where": "host cores"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{args.steps} steps x {batch} crops after {args.warmup} warm-up, {what} on torch {torch.__version__} "
+                                   f"CPU ATen (oneDNN), {threads} threads of {cores} cores"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -506,13 +533,16 @@ def run_b200(args):
     cpu = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        rate0, _ = cpu_reference_rate(bands, classes, 64, args.regime, 1, 1, cores)
+        ref_model = reference_module(bands, classes)
+        rate0, _ = cpu_reference_rate(bands, classes, 64, args.regime, 1, 1, cores, ref_model)
         cb = B
         while cb > 64 and 3 * cb / rate0 > 25.0:
             cb //= 2
-        rate, _ = cpu_reference_rate(bands, classes, cb, args.regime, 2, 1, cores)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"2 timed steps x {cb} crops (1 warm-up) of the same workload, oracle port on torch {torch.__version__} CPU ATen, {cores} threads"}
+        rate, _ = cpu_reference_rate(bands, classes, cb, args.regime, 2, 1, cores, ref_model)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": ref_model[1],
+               "sample": f"2 timed steps x {cb} crops (1 warm-up) of the same workload, "
+                         + ("the reference's own src/models/Hang2020.py" if ref_model[1] == "reference" else "oracle port")
+                         + f" on torch {torch.__version__} CPU ATen, {cores} threads"}
 
     torch_gpu = torch_eager_gpu_baseline(args) if (world == 1 and not args.no_cpu) else None
 
@@ -520,8 +550,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"Hang2020(bands={bands}, classes={classes}) fwd+CE({args.regime})+bwd"
-                               + ("+grad all-reduce" if world > 1 else "") + f", {B} crops per GPU per step",
+        "config": {"workload": workload_string(args, world),
                    "regime": args.regime, "launch": "cuda-graph replay" if args.graph else "eager", "batch_per_gpu": B, "global_batch": B * world,
                    "side_stream_overlap": int(args.overlap), "programmatic_dependent_launch": bool(args.pdl), "parallelism": f"dp{world}", "gradient_exchange": sync.last_path if world > 1 else None, "l2": f"crops per step = {B * bands * 484 / 1e6:.0f} MB > 126 MB L2 (no flush needed)"
                    if B * bands * 484 > 126e6 else "flush: none (inputs smaller than L2)"},

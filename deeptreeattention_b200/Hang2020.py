@@ -81,6 +81,7 @@ class _NetSpec:
         # optional persistent (flat float32, 0-dim float64) gradient buffers supplied by distributed.GradSync: symmetric
         # memory that the peer all-reduce kernel works on in place
         self.grad_buffers = None
+        self.last_saved = None          # diagnostics only (_capi.KEEP_SAVED)
         self._table_key = None
         self._table = None
 
@@ -120,6 +121,7 @@ class _FusedNetFunction(torch.autograd.Function):
                                  joint.data_ptr() if joint is not None else None, saved.data_ptr(), work.data_ptr(),
                                  _stream_ptr(dev))
         _capi.check(handle, rc, "dta_forward")
+        spec.last_saved = saved if _capi.KEEP_SAVED else None
         ctx.spec, ctx.training, ctx.names, ctx.buffers = spec, training, names, buffers
         ctx.save_for_backward(x, saved, *params)
         ctx.set_materialize_grads(False)

@@ -66,7 +66,7 @@ class StageTime(C.Structure):
 
 
 EXPORTS = ["dta_abi_version", "dta_create", "dta_destroy", "dta_last_error", "dta_set_option", "dta_get_option",
-           "dta_profile_read", "dta_query_sizes", "dta_forward", "dta_backward", "dta_loss_workspace_bytes",
+           "dta_profile_read", "dta_query_sizes", "dta_saved_region", "dta_forward", "dta_backward", "dta_loss_workspace_bytes",
            "dta_cross_entropy_heads", "dta_preprocess_crops", "dta_grad_allreduce_sizes", "dta_grad_allreduce",
            "dta_plane_mean", "dta_plane_mean_backward", "dta_conv_module_workspace_bytes", "dta_conv_module_forward",
            "dta_conv_module_backward", "dta_attention_sizes", "dta_attention_forward", "dta_attention_backward",
@@ -146,6 +146,8 @@ def lib():
         L.dta_profile_read.restype = C.c_int
         L.dta_query_sizes.argtypes = [C.POINTER(Shape), C.POINTER(Sizes)]
         L.dta_query_sizes.restype = C.c_int
+        L.dta_saved_region.argtypes = [C.POINTER(Shape), C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.dta_saved_region.restype = C.c_int
         L.dta_forward.argtypes = [C.c_void_p, C.POINTER(Shape), C.c_void_p, C.POINTER(Tensors),
                                   C.POINTER(C.c_void_p * 6), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.dta_forward.restype = C.c_int
@@ -183,7 +185,7 @@ def lib():
         L.dta_forward_pair.argtypes = [vp, C.POINTER(Shape), ci, vp, C.POINTER(Tensors), C.POINTER(C.c_void_p * 6), vp, vp, vp]
         L.dta_crops_nonzero.argtypes = [vp, ci, C.POINTER(C.c_void_p * 16), sz, vp, vp, vp]
         L.dta_ensemble_mean.argtypes = [vp, ci, C.POINTER(C.c_void_p * 16), vp, ci, ci, ci, vp, vp]
-        for name in EXPORTS[15:]:
+        for name in EXPORTS[16:]:
             getattr(L, name).restype = C.c_int
         _lib = L
         return L
@@ -225,6 +227,20 @@ def query_sizes(net_kind: int, batch: int, bands: int, classes: int, training: b
     if rc != DTA_OK:
         raise ValueError(f"dta_query_sizes rejected shape (kind={net_kind}, batch={batch}, bands={bands}, classes={classes})")
     return out
+
+
+def saved_region(net_kind: int, batch: int, bands: int, classes: int, training: bool, block: int):
+    """(byte offset, float count) of convolution block ``block``'s output inside a forward's ``saved`` buffer (diagnostic)."""
+    s = Shape(net_kind, batch, bands, classes, int(training))
+    off, n = C.c_size_t(), C.c_size_t()
+    if lib().dta_saved_region(C.byref(s), block, C.byref(off), C.byref(n)) != DTA_OK:
+        raise ValueError("dta_saved_region rejected the shape / block")
+    return off.value, n.value
+
+
+# Diagnostics (parity tests): when True, every fused forward leaves a reference to its ``saved`` buffer in the module's
+# spec (``model.fused_spec().last_saved``) so that the convolution outputs can be read back with ``saved_region``.
+KEEP_SAVED = False
 
 
 def set_option(device_index: int, key: str, value: int):

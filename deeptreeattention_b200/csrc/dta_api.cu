@@ -510,6 +510,17 @@ int dta_query_sizes(const dta_shape* shape, dta_sizes* out) {
   return DTA_OK;
 }
 
+int dta_saved_region(const dta_shape* shape, int block, size_t* offset_bytes, size_t* n_floats) {
+  NetDesc d;
+  if (!shape || !offset_bytes || !n_floats || !describe(shape->net_kind, &d)) return DTA_ERR_INVALID_ARG;
+  if (shape->batch <= 0 || shape->bands <= 0 || shape->classes <= 0 || block < 0 || block > 2) return DTA_ERR_INVALID_ARG;
+  char* const base = reinterpret_cast<char*>(uintptr_t(256));   // any non-null base: only differences are used
+  const SavedLayout L = layout_saved(*shape, d, base);
+  *offset_bytes = (size_t)(reinterpret_cast<char*>(L.z[block]) - base);
+  *n_floats = (size_t)shape->batch * d.nb * kC[block] * kHWpre[block];
+  return DTA_OK;
+}
+
 // Shared body of dta_forward and dta_forward_pair (classes_second > 0: branch 1's heads have that many classes).
 static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second, const float* x, const dta_tensors* params,
                         float* const scores[6], float* joint, void* saved, void* workspace, void* cuda_stream) {

@@ -198,14 +198,28 @@ def make_inputs(batch: int, bands: int, classes: int, seed: int, dist: str = "un
 
 
 # --------------------------------------------------------------------------- forward
-def conv_block(p: Params, prefix: str, u: torch.Tensor, pool: bool, training: bool) -> torch.Tensor:
+Z_RECORD: Optional[Dict[str, torch.Tensor]] = None   # tests: set to a dict to collect every block's convolution output
+
+
+def conv_block(p: Params, prefix: str, u: torch.Tensor, pool: bool, training: bool,
+               z_values: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
     """conv3x3 'same' -> BatchNorm2d -> ReLU -> optional 2x2 floor max-pool.
 
     Follows conv_module.forward, Hang2020.py:24-31 (layers declared :18-22).  In
     training mode F.batch_norm updates running_mean/var in place (momentum 0.1,
     unbiased variance) and num_batches_tracked is bumped like nn.BatchNorm2d does.
+
+    ``z_values`` (tests only): ``{prefix: tensor}`` of convolution outputs measured on another implementation.  The
+    block then continues from THOSE values while gradients still flow through this oracle's own convolution
+    (value substitution, derivative unchanged): every ReLU / max-pool decision downstream is taken on the same
+    numbers as in the implementation under test, which is what makes a gradient comparison well defined for a
+    piecewise-linear network (see tests/test_gpu_parity.py).
     """
     z = F.conv2d(u, p[f"{prefix}.conv_layer.weight"], p[f"{prefix}.conv_layer.bias"], padding=1)
+    if Z_RECORD is not None:
+        Z_RECORD[prefix] = z.detach().clone()
+    if z_values is not None and prefix in z_values:
+        z = z + (z_values[prefix].to(z.dtype) - z).detach()
     a = F.batch_norm(z, p[f"{prefix}.bn1.running_mean"], p[f"{prefix}.bn1.running_var"],
                      p[f"{prefix}.bn1.weight"], p[f"{prefix}.bn1.bias"],
                      training=training, momentum=BN_MOMENTUM, eps=BN_EPS)
@@ -250,38 +264,38 @@ def spatial_gate(p: Params, prefix: str, r: torch.Tensor) -> Tuple[torch.Tensor,
     return out, feat
 
 
-def branch_forward(p: Params, prefix: str, attn: str, x: torch.Tensor, training: bool) -> List[torch.Tensor]:
+def branch_forward(p: Params, prefix: str, attn: str, x: torch.Tensor, training: bool, z_values=None) -> List[torch.Tensor]:
     """Three (conv block -> attention -> head) stages; returns the three head scores.
     spectral_network.forward Hang2020.py:226-240 / spatial_network.forward :190-204."""
     gate = spectral_gate if attn == "spectral" else spatial_gate
     scores = []
     u = x
     for k in (1, 2, 3):
-        r = conv_block(p, f"{prefix}conv{k}", u, pool=(k > 1), training=training)
+        r = conv_block(p, f"{prefix}conv{k}", u, pool=(k > 1), training=training, z_values=z_values)
         u, feat = gate(p, f"{prefix}attention_{k}", r)
         scores.append(F.linear(feat, p[f"{prefix}classifier{k}.fc1.weight"],
                                p[f"{prefix}classifier{k}.fc1.bias"]))   # Classifier, :63-66
     return scores
 
 
-def forward(kind: str, p: Params, x: torch.Tensor, training: bool):
+def forward(kind: str, p: Params, x: torch.Tensor, training: bool, z_values=None):
     """Returns (result, heads): ``result`` is what the reference module returns
     (joint scores for hang2020 :251-263, list of 3 for the sub-networks, scores for
     vanilla_CNN :45-53); ``heads`` is the list of every head's scores in branch-major
     order (spectral 1-3 then spatial 1-3 for hang2020)."""
     if kind == "hang2020":
-        spec = branch_forward(p, "spectral_network.", "spectral", x, training)
-        spat = branch_forward(p, "spatial_network.", "spatial", x, training)
+        spec = branch_forward(p, "spectral_network.", "spectral", x, training, z_values)
+        spat = branch_forward(p, "spatial_network.", "spatial", x, training, z_values)
         w = torch.sigmoid(p["alpha"])                     # float64 0-dim, :259
         joint = spec[-1] * w + spat[-1] * (1 - w)         # float32 result, :260
         return joint, spec + spat
     if kind in ("spectral", "spatial"):
-        heads = branch_forward(p, "", kind, x, training)
+        heads = branch_forward(p, "", kind, x, training, z_values)
         return heads, heads
     if kind == "vanilla":
         u = x
         for k in (1, 2, 3):
-            u = conv_block(p, f"conv{k}", u, pool=(k > 1), training=training)
+            u = conv_block(p, f"conv{k}", u, pool=(k > 1), training=training, z_values=z_values)
         s = F.linear(torch.flatten(u, start_dim=1), p["fc1.weight"], p["fc1.bias"])
         return s, [s]
     raise ValueError(f"unknown net kind {kind!r}")
@@ -305,14 +319,14 @@ def loss_regime(regime: str, result, heads, y, weight=None):
 
 
 def step(kind: str, params: Params, x, y, regime: str = "R1", training: bool = True,
-         weight=None, num_threads: Optional[int] = None):
+         weight=None, num_threads: Optional[int] = None, z_values=None):
     """One forward + loss + backward.  Returns (loss, result, heads, grads) with grads a
     ``{name: tensor-or-None}`` table over the trainable parameters."""
     if num_threads:
         torch.set_num_threads(num_threads)
     p = {k: (v.clone().requires_grad_(True) if not is_buffer(k) else v.clone())
          for k, v in params.items()}
-    result, heads = forward(kind, p, x, training)
+    result, heads = forward(kind, p, x, training, z_values)
     loss = loss_regime(regime, result, heads, y, weight)
     names = [k for k in p if not is_buffer(k)]
     grads = torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)

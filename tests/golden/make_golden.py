@@ -14,8 +14,9 @@ that lies within fp32 rounding noise of a kink can fall on either side under a d
 summation order, which changes individual gradient elements by O(1e-2) relative -- in the
 reference itself too (CPU oneDNN vs cuDNN).  Element-wise gradient parity at 1e-3 is only
 defined away from kinks, so every case's seed is advanced until the reference's gradients are
-stable (5e-4 relative) under three random 3e-6 relative perturbations of crops and weights
-(the noise level of an fp32 evaluation with a different summation order).  The accepted seed
+stable (5e-4 relative) under three random 1e-5 relative perturbations of crops and weights
+(above the 2^-18 = 3.8e-6 operand rounding of the split-bf16 tensor-core convolutions, and far above
+the noise of an fp32 evaluation with a different summation order).  The accepted seed
 is recorded in cases.json and the measured per-tensor sensitivity is stored next to each
 gradient (``grad/<name>/sens``) so tests can widen the tolerance by the reference's own
 conditioning instead of guessing.
@@ -70,7 +71,7 @@ def sample_index(n):
     return np.unique(np.linspace(0, n - 1, SAMPLE).astype(np.int64))
 
 
-def kink_stable(ref, case, seed, eps=3e-6, tol=5e-4, draws=3):
+def kink_stable(ref, case, seed, eps=1e-5, tol=5e-4, draws=3):
     """(stable, {name: sensitivity}): whether the reference's gradients move smoothly under
     tiny perturbations, and by how much each tensor moved."""
     name, kind, bands, classes, batch, dist, regime, training, perturb, _ = case

@@ -103,3 +103,35 @@ def l2_conditioning(kind, table, x, y, regime, training, base_grads64, eps=1e-5,
         for k in cond:
             cond[k] = max(cond[k], rel_l2(g2[k], base_grads64[k]))
     return cond
+
+
+# ----------------------------------------------------------------------------- decision-matched oracle
+_KIND_ID = {"hang2020": 0, "spectral": 1, "spatial": 2, "vanilla": 3}
+
+
+def cuda_conv_outputs(model, kind, batch, bands, classes, training):
+    """``{oracle block prefix: z}``: the three convolution outputs (pre-BatchNorm, bias included) the CUDA forward just left
+    in its ``saved`` buffer (``dta_saved_region``; needs ``_capi.KEEP_SAVED``), split per branch, on the CPU."""
+    from deeptreeattention_b200 import _capi
+    saved = model.fused_spec().last_saved
+    assert saved is not None, "set _capi.KEEP_SAVED before the forward"
+    out = {}
+    nb = 2 if kind == "hang2020" else 1
+    for blk, (c, s) in enumerate(((32, 11), (64, 11), (128, 5))):
+        off, n = _capi.saved_region(_KIND_ID[kind], batch, bands, classes, training, blk)
+        z = saved[off:off + 4 * n].view(torch.float32).view(batch, nb * c, s, s).cpu()
+        if kind == "hang2020":
+            out[f"spectral_network.conv{blk + 1}"] = z[:, :c].contiguous()
+            out[f"spatial_network.conv{blk + 1}"] = z[:, c:].contiguous()
+        else:
+            out[f"conv{blk + 1}"] = z
+    return out
+
+
+def matched_oracle_step_fp64(kind, table, x, y, regime, training, z_values):
+    """The float64 oracle continued from the convolution outputs of the implementation under test (value substitution only;
+    every derivative is the oracle's own).  A Hang2020 network is piecewise linear in its activations: its gradient is only
+    comparable between two evaluations that sit on the same linear piece, i.e. take the same ReLU / max-pool decisions.
+    Forward parity (scores against the UNMATCHED oracle) bounds how far the substituted values are from the oracle's own."""
+    return orc.step(kind, to_fp64(table), x.double(), y, regime=regime, training=training,
+                    z_values={k: v.double() for k, v in z_values.items()})

@@ -91,3 +91,30 @@ def test_fp32_reference_arithmetic_vs_fp64_conditioning():
         if g is None or k.endswith("conv_layer.bias"):
             continue
         assert gu.rel_l2(g32[k], g) <= 1e-4 + 4.0 * cond[k], k
+
+
+def test_decision_matched_oracle_isolates_the_kinks():
+    """The mechanism behind the GPU gradient tests: continue the float64 oracle from ANOTHER evaluation's convolution
+    outputs (here the float32 oracle's) and the two gradients agree to rounding (1e-5 relative L2, every tensor), although
+    the unmatched float64 gradients differ by more on the tensors behind a flipped ReLU / max-pool decision."""
+    torch.set_num_threads(8)
+    kind, bands, classes, batch = "hang2020", 40, 6, 256
+    table = orc.init_params(kind, bands, classes, 3, perturb_bn=True)
+    x, y = orc.make_inputs(batch, bands, classes, 3)
+    orc.Z_RECORD = {}
+    try:
+        g32 = orc.step(kind, table, x, y, regime="R2", training=True)[3]
+        z32 = dict(orc.Z_RECORD)
+    finally:
+        orc.Z_RECORD = None
+    assert len(z32) == 6
+    g64 = gu.oracle_step_fp64(kind, table, x, y, "R2", True)[3]
+    gm = gu.matched_oracle_step_fp64(kind, table, x, y, "R2", True, z32)[3]
+    worst_matched = worst_plain = 0.0
+    for k, g in gm.items():
+        if g is None or k.endswith("conv_layer.bias"):
+            continue
+        worst_matched = max(worst_matched, gu.rel_l2(g32[k], g))
+        worst_plain = max(worst_plain, gu.rel_l2(g32[k], g64[k]))
+    assert worst_matched <= 1e-5, worst_matched
+    assert worst_matched <= worst_plain

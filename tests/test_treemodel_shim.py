@@ -1,0 +1,110 @@
+"""Drop-in demonstration: the CUDA ``Hang2020`` handed to a ``TreeModel``-shaped caller
+(tests/treemodel_shim.py restates /root/reference/src/main.py:33-94,135-163 without Lightning) trains like the reference
+module does on the CPU -- same loss trajectory over Adam steps, same ``state_dict`` contract, same predictions.
+
+The comparison model is the REFERENCE'S OWN ``src/models/Hang2020.py`` when a copy is available (``/root/reference`` in the
+build container, ``oracle/_ref`` on the GPU box; oracle/ref_loader.py), else the oracle port."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hang2020_oracle as orc
+from oracle import ref_loader
+from treemodel_shim import TreeModel
+
+BANDS, CLASSES, BATCH, STEPS = 369, 50, 24, 5
+
+
+def reference_model(table):
+    """(module, "reference" | "port") with the reference's parameter names, loaded from ``table``, on the CPU."""
+    ref = ref_loader.load("Hang2020")
+    if ref is not None:
+        m = ref.Hang2020(BANDS, CLASSES)
+        m.load_state_dict(table, strict=True)
+        return m, "reference"
+    m = orc.OracleModule("hang2020", BANDS, CLASSES, seed=0)
+    m.load_table(table)
+    return m, "port"
+
+
+def make_batches(device):
+    out = []
+    for i in range(STEPS + 1):
+        x, y = orc.make_inputs(BATCH, BANDS, CLASSES, 300 + i)
+        out.append((["id"] * BATCH, {"HSI": x.to(device)}, y.to(device)))
+    return out
+
+
+def loss_weights():
+    rng = np.random.Generator(np.random.PCG64(17))
+    return rng.uniform(0.5, 2.0, size=CLASSES).tolist()
+
+
+def test_shim_runs_the_reference_module_on_cpu():
+    """The shim itself, with the comparison model only (no CUDA): losses finite, the scheduler saw the validation loss,
+    predict returns (B, classes).  Keeps the shim honest on the CPU suite."""
+    torch.set_num_threads(8)
+    table = orc.init_params("hang2020", BANDS, CLASSES, 31)
+    m, kind = reference_model(table)
+    tm = TreeModel(m, CLASSES, {f"sp{i}": i for i in range(CLASSES)}, loss_weight=loss_weights(), config={"lr": 1e-4, "top_k": 1})
+    batches = make_batches("cpu")
+    losses = tm.fit_steps(batches[:2], val_batch=batches[-1])
+    assert len(losses) == 2 and all(np.isfinite(losses))
+    assert len(tm.logged["val_loss"]) == 1 and tm.scheduler.best == pytest.approx(tm.logged["val_loss"][0])
+    m.eval()
+    with torch.no_grad():
+        assert tuple(tm.predict({"HSI": batches[0][1]["HSI"]}).shape) == (BATCH, CLASSES)
+
+
+@pytest.mark.gpu
+def test_cuda_module_drops_into_treemodel():
+    from deeptreeattention_b200 import Hang2020 as H
+    torch.set_num_threads(8)
+    table = orc.init_params("hang2020", BANDS, CLASSES, 31)
+    label_dict = {f"sp{i}": i for i in range(CLASSES)}
+    cfg = {"lr": 1e-4, "top_k": 1}
+
+    ref, kind = reference_model(table)
+    tm_ref = TreeModel(ref, CLASSES, label_dict, loss_weight=loss_weights(), config=cfg)
+    ours = H.Hang2020(BANDS, CLASSES)
+    ours.load_state_dict(table)
+    ours = ours.cuda()
+    tm = TreeModel(ours, CLASSES, label_dict, loss_weight=loss_weights(), config=cfg)
+    assert tm.loss_weight.is_cuda
+
+    # same state_dict contract before training (keys, order, shapes, dtypes)
+    if kind == "reference":
+        sd_r, sd_o = ref.state_dict(), ours.state_dict()
+        assert list(sd_r.keys()) == list(sd_o.keys())
+        for k in sd_r:
+            assert sd_r[k].shape == sd_o[k].shape and sd_r[k].dtype == sd_o[k].dtype, k
+
+    cpu_batches, gpu_batches = make_batches("cpu"), make_batches("cuda")
+    losses_ref = tm_ref.fit_steps(cpu_batches[:STEPS], val_batch=cpu_batches[-1])
+    losses = tm.fit_steps(gpu_batches[:STEPS], val_batch=gpu_batches[-1])
+    np.testing.assert_allclose(losses, losses_ref, rtol=0, atol=1e-4)          # five Adam steps, same trajectory
+    assert losses[-1] < losses[0]
+    assert abs(tm.logged["val_loss"][0] - tm_ref.logged["val_loss"][0]) < 2e-3  # eval mode: running statistics after 5 updates
+    assert tm.optimizer.param_groups[0]["lr"] == tm_ref.optimizer.param_groups[0]["lr"]
+
+    # trained parameters agree (Adam moves every element by ~lr per step whatever the gradient's size, so elements whose true
+    # gradient is rounding noise -- conv biases under batch statistics -- are compared on what they do, below, not here)
+    tr = ref.table() if kind == "port" else dict(ref.state_dict())
+    for k, v in ours.state_dict().items():
+        if orc.is_buffer(k) or k.endswith("conv_layer.bias"):
+            continue
+        d = float((v.detach().cpu().double() - tr[k].detach().double()).abs().max())
+        assert d <= 2.5e-4, f"{k}: trained parameter differs by {d:.2e}"
+
+    # state_dict round trip: the reference-trained weights load into the CUDA module and predict alike
+    state = {k: v.detach().clone() for k, v in tr.items()}
+    fresh = H.Hang2020(BANDS, CLASSES)
+    fresh.load_state_dict(state)
+    fresh = fresh.cuda().eval()
+    tm2 = TreeModel(fresh, CLASSES, label_dict, config=cfg)
+    ref.eval()
+    with torch.no_grad():
+        pred = tm2.predict({"HSI": cpu_batches[0][1]["HSI"]})
+        pred_ref = tm_ref.predict({"HSI": cpu_batches[0][1]["HSI"]})
+    assert pred.device.type == "cpu"
+    np.testing.assert_allclose(pred.numpy(), pred_ref.numpy(), rtol=0, atol=1e-3)
