@@ -2,6 +2,7 @@
 // fused Adam step: argument checks and launch sequences for the kernels of dta_blocks.cuh.  Contract: include/dta_b200.h.
 #include "dta_blocks.cuh"
 #include "dta_ctx.cuh"
+#include "dta_metadata.cuh"
 
 using namespace dta;
 
@@ -361,6 +362,102 @@ int dta_adam_step(dta_ctx* ctx, int n_tensors, float* const params[], const floa
   adam_step_kernel<<<chunks > 0 ? chunks : 1, kBlkThreads, 0, st>>>(tab, hy, reinterpret_cast<const long long*>(step_device), lr_device, exp_avg,
                                                                    exp_avg_sq, param64, grad64, moments64);
   DTA_CHECK_LAUNCH(ctx, "adam_step");
+  return DTA_OK;
+}
+
+// ---- metadata / metadata_sensor_fusion (src/models/metadata.py:9-44) -----------------------------------------------
+int dta_metadata_sizes(int batch, int classes, size_t* saved_bytes, size_t* workspace_bytes) {
+  if (batch <= 0 || classes <= 0 || !saved_bytes || !workspace_bytes) return DTA_ERR_INVALID_ARG;
+  *saved_bytes = meta_saved_layout(nullptr, batch, classes).floats * sizeof(float);
+  *workspace_bytes = meta_work_layout(nullptr, batch, classes).floats * sizeof(float);
+  return DTA_OK;
+}
+
+static MetaTensors meta_tensors(const dta_metadata_tensors* t) {
+  MetaTensors m{};
+  m.emb = t->embedding; m.bn_w = t->bn_w; m.bn_b = t->bn_b; m.bn_rm = t->bn_rm; m.bn_rv = t->bn_rv;
+  m.bn_nbt = reinterpret_cast<long long*>(t->bn_nbt);
+  m.mlp_w = t->mlp_w; m.mlp_b = t->mlp_b; m.fc_w = t->fc_w; m.fc_b = t->fc_b;
+  return m;
+}
+
+static int meta_check(dta_ctx* ctx, int batch, int sites, int classes, const int64_t* site, const float* sensor,
+                      const dta_metadata_tensors* p, int need_running) {
+  if (batch <= 0 || sites <= 0 || classes <= 0) return fail(ctx, DTA_ERR_INVALID_ARG, "batch, sites and classes must be positive");
+  if (classes > 4096) return fail(ctx, DTA_ERR_UNSUPPORTED, "classes > 4096 not supported");
+  if (!site || !p) return fail(ctx, DTA_ERR_INVALID_ARG, "site and params are required");
+  if (!p->embedding || !p->bn_w || !p->bn_b || !p->mlp_w || !p->mlp_b) return fail(ctx, DTA_ERR_INVALID_ARG, "metadata parameter is NULL");
+  if (need_running && (!p->bn_rm || !p->bn_rv)) return fail(ctx, DTA_ERR_INVALID_ARG, "BatchNorm1d running statistics are NULL");
+  if (sensor && (!p->fc_w || !p->fc_b)) return fail(ctx, DTA_ERR_INVALID_ARG, "fusion layer parameter is NULL");
+  return DTA_OK;
+}
+
+int dta_metadata_forward(dta_ctx* ctx, int batch, int sites, int classes, int training, const int64_t* site, const float* sensor,
+                         const dta_metadata_tensors* params, const uint8_t* keep_mask, uint64_t seed, float* out, void* saved,
+                         void* cuda_stream) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  int rc = meta_check(ctx, batch, sites, classes, site, sensor, params, !training);
+  if (rc != DTA_OK) return rc;
+  if (!out || !saved) return fail(ctx, DTA_ERR_INVALID_ARG, "out and saved are required");
+  if ((rc = begin_call(ctx)) != DTA_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  StageScope sc(ctx, "meta.forward", st);
+  const MetaTensors p = meta_tensors(params);
+  const MetaSaved sv = meta_saved_layout(saved, batch, classes);
+  const long long* sidx = reinterpret_cast<const long long*>(site);
+  meta_bn_stats_kernel<<<1, kMetaStatThreads, 0, st>>>(sidx, batch, sites, p, training, sv.mean, sv.istd);
+  DTA_CHECK_LAUNCH(ctx, "meta_bn_stats");
+  const size_t smem = sizeof(float) * kMetaCrops * (kMetaDim + 2 * (size_t)classes);
+  cudaFuncSetAttribute(meta_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  meta_fwd_kernel<<<(batch + kMetaCrops - 1) / kMetaCrops, kMetaThreads, smem, st>>>(sidx, sensor, batch, sites, classes, p, training, keep_mask,
+                                                                                  (unsigned long long)seed, sv, out);
+  DTA_CHECK_LAUNCH(ctx, "meta_fwd");
+  return DTA_OK;
+}
+
+int dta_metadata_backward(dta_ctx* ctx, int batch, int sites, int classes, int training, const int64_t* site, const float* sensor,
+                          const dta_metadata_tensors* params, const void* saved, const float* out, const float* dout,
+                          const dta_metadata_tensors* grads, float* dsensor, void* workspace, void* cuda_stream) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  int rc = meta_check(ctx, batch, sites, classes, site, sensor, params, 0);
+  if (rc != DTA_OK) return rc;
+  if (!saved || !out || !dout || !grads || !workspace) return fail(ctx, DTA_ERR_INVALID_ARG, "saved, out, dout, grads and workspace are required");
+  if ((rc = begin_call(ctx)) != DTA_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  StageScope sc(ctx, "meta.backward", st);
+  const MetaTensors p = meta_tensors(params);
+  const MetaSaved sv = meta_saved_layout(const_cast<void*>(saved), batch, classes);
+  const MetaWork wk = meta_work_layout(workspace, batch, classes);
+  const long long* sidx = reinterpret_cast<const long long*>(site);
+  const int fused = sensor != nullptr;
+  const int C = classes;
+  const size_t smem = sizeof(float) * kMetaCrops * 2 * (size_t)C;
+  cudaFuncSetAttribute(meta_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  meta_bwd_rows_kernel<<<(batch + kMetaCrops - 1) / kMetaCrops, kMetaThreads, smem, st>>>(sidx, batch, sites, C, fused, p, sv, out, dout, wk, dsensor);
+  DTA_CHECK_LAUNCH(ctx, "meta_bwd_rows");
+  if (fused) {
+    // dfc_w[i][j] = sum_b U1[b][i] * cat[b][j], cat = [m | sensor]
+    if (grads->fc_w) {
+      batch_sum(ctx, st, wk.u1, C, sv.m, C, batch, C, C, grads->fc_w, 2 * (size_t)C, 1);
+      batch_sum(ctx, st, wk.u1, C, sensor, C, batch, C, C, grads->fc_w + C, 2 * (size_t)C, 1);
+    }
+    batch_sum(ctx, st, wk.u1, C, nullptr, 0, batch, C, 1, grads->fc_b, 1, 0);
+  }
+  batch_sum(ctx, st, wk.u2, C, sv.d, kMetaDim, batch, C, kMetaDim, grads->mlp_w, kMetaDim, 1);
+  batch_sum(ctx, st, wk.u2, C, nullptr, 0, batch, C, 1, grads->mlp_b, 1, 0);
+  batch_sum(ctx, st, wk.dyx, kMetaDim, nullptr, 0, batch, kMetaDim, 1, wk.dgamma, 1, 0);
+  batch_sum(ctx, st, wk.dy, kMetaDim, nullptr, 0, batch, kMetaDim, 1, wk.dbeta, 1, 0);
+  if (grads->bn_w || grads->bn_b) {
+    meta_copy16_kernel<<<1, 32, 0, st>>>(wk.dgamma, grads->bn_w, wk.dbeta, grads->bn_b);
+    DTA_CHECK_LAUNCH(ctx, "meta_copy16");
+  }
+  if (grads->embedding) {
+    const int total = sites * kMetaDim;
+    meta_bwd_embed_kernel<<<(total + 127) / 128, 128, 0, st>>>(sidx, batch, sites, p, sv, wk, training, grads->embedding);
+    DTA_CHECK_LAUNCH(ctx, "meta_bwd_embed");
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("metadata backward: ") + cudaGetErrorString(e));
   return DTA_OK;
 }
 

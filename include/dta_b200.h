@@ -258,6 +258,40 @@ int dta_crops_nonzero(dta_ctx* ctx, int n_years, const float* const crops[], siz
 int dta_ensemble_mean(dta_ctx* ctx, int n_years, const float* const scores[], const float* flags, int batch, int classes,
                       int softmax, float* out, void* cuda_stream);
 
+/*
+ * Site metadata branch and late fusion (BASELINE config 5).  Replaces metadata.forward and the layers after the sensor
+ * model in metadata_sensor_fusion.forward (src/models/metadata.py:17-24, 37-44):
+ *   meta  = relu(Linear(16, classes)(Dropout(0.7)(BatchNorm1d(16)(Embedding(sites, 16)(site)))))
+ *   out   = relu(Linear(2*classes, classes)(cat([meta, sensor], 1)))        (sensor = Hang2020 joint scores, dta_forward)
+ * With sensor == NULL the call is the stand-alone `metadata` module (out = meta; fc_w / fc_b unused).
+ *   site      : (batch) int64 site index, device memory; values outside [0, sites) are clamped (nn.Embedding raises)
+ *   params    : device pointers of the state_dict tensors; training != 0 updates bn_rm / bn_rv / bn_nbt
+ *   keep_mask : (batch, 16) uint8, non-zero = element kept by the dropout, or NULL: the mask is drawn from a counter-based
+ *               generator keyed by `seed`.  Ignored in eval mode (dropout is the identity)
+ *   saved     : saved_bytes; backward needs it together with the same site / sensor and the forward's `out`
+ * Backward: `grads` entries may be NULL (skipped); dsensor (batch, classes) is the gradient to hand to dta_backward as
+ * `djoint` (NULL when sensor was NULL).  All reductions run in fixed order.
+ */
+typedef struct dta_metadata_tensors {
+  float* embedding;  /* (sites, 16)                      metadata_model.embedding.weight */
+  float* bn_w;       /* (16)                             metadata_model.batch_norm.weight */
+  float* bn_b;
+  float* bn_rm;      /* running_mean / running_var / num_batches_tracked (ignored in a gradient table) */
+  float* bn_rv;
+  int64_t* bn_nbt;
+  float* mlp_w;      /* (classes, 16)                    metadata_model.mlp.weight */
+  float* mlp_b;
+  float* fc_w;       /* (classes, 2*classes)             fc1.weight (fusion only) */
+  float* fc_b;
+} dta_metadata_tensors;
+int dta_metadata_sizes(int batch, int classes, size_t* saved_bytes, size_t* workspace_bytes);
+int dta_metadata_forward(dta_ctx* ctx, int batch, int sites, int classes, int training, const int64_t* site, const float* sensor,
+                         const dta_metadata_tensors* params, const uint8_t* keep_mask, uint64_t seed, float* out, void* saved,
+                         void* cuda_stream);
+int dta_metadata_backward(dta_ctx* ctx, int batch, int sites, int classes, int training, const int64_t* site, const float* sensor,
+                          const dta_metadata_tensors* params, const void* saved, const float* out, const float* dout,
+                          const dta_metadata_tensors* grads, float* dsensor, void* workspace, void* cuda_stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Stand-alone building blocks.  The reference's tests and notebooks call conv_module, spatial_attention,
  * spectral_attention and Classifier on their own (tests/test_Hang2020.py:8-33); inside the networks they run fused

@@ -298,28 +298,6 @@ def test_year_ensemble_matches_oracle_and_skips_zero_years():
     np.testing.assert_allclose(out.numpy(), ref.numpy(), rtol=0, atol=SCORE_TOL)
 
 
-def test_metadata_sensor_fusion_matches_torch_reference():
-    """metadata_sensor_fusion (src/models/metadata.py:26-44, shapes of tests/test_metadata.py) in eval mode: the
-    Hang2020 part against the oracle, the site MLP / fusion layer with the same torch layers on the CPU."""
-    from deeptreeattention_b200 import metadata as M
-    bands, sites, classes, B = 30, 5, 10, 20
-    torch.manual_seed(1)
-    m = M.metadata_sensor_fusion(bands=bands, sites=sites, classes=classes).eval()
-    x, _ = orc.make_inputs(B, bands, classes, 9, "normal")
-    site = torch.randint(0, sites, (B,))
-    table = {k: v.detach().clone() for k, v in m.sensor_model.state_dict().items()}
-    joint, _ = orc.forward("hang2020", table, x, training=False)
-    with torch.no_grad():
-        ref = torch.relu(m.fc1(torch.cat([m.metadata_model(site), joint], dim=1)))
-        got = m.cuda()(x.cuda(), site.cuda()).cpu()
-    assert got.shape == (B, classes)
-    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=0, atol=SCORE_TOL)
-    m.train()
-    out = m(x.cuda(), site.cuda())
-    out.sum().backward()
-    assert m.sensor_model.alpha.grad is not None and m.fc1.weight.grad is not None
-
-
 def test_wide_head_and_odd_sizes_match_oracle():
     """More classes than one 32-wide reduction tile and than a warp, bands not a multiple of 8 or 16, odd batch."""
     kind, bands, classes, batch = "hang2020", 21, 130, 7
