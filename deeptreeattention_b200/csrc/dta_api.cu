@@ -491,6 +491,7 @@ int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value) {
   if (!ctx || !key || !value) return DTA_ERR_INVALID_ARG;
   if (!strcmp(key, "conv_impl")) { *value = ctx->conv_impl; return DTA_OK; }
   if (!strcmp(key, "launches")) { *value = ctx->launches; return DTA_OK; }
+  if (!strcmp(key, "launches_total")) { *value = ctx->launches_total + ctx->launches; return DTA_OK; }
   if (!strcmp(key, "profile")) { *value = ctx->profile; return DTA_OK; }
   if (!strcmp(key, "sm_count")) { *value = ctx->sm_count; return DTA_OK; }
   if (!strcmp(key, "overlap")) { *value = ctx->overlap; return DTA_OK; }
@@ -538,7 +539,7 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
-  ctx->launches = 0;
+  ctx->launches_total += ctx->launches; ctx->launches = 0;
   pdl_enabled() = ctx->pdl;
 
   const int B = shape->batch, nb = d.nb, bands = shape->bands, classes = shape->classes;
@@ -747,7 +748,7 @@ int dta_preprocess_crops(dta_ctx* ctx, const int16_t* raw, int batch, int bands_
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
-  ctx->launches = 0;
+  ctx->launches_total += ctx->launches; ctx->launches = 0;
   pdl_enabled() = ctx->pdl;
   StageScope sc(ctx, "data.preprocess_crops", st);
   launch_k(preprocess_crops_kernel, batch, 128 * kPrepSlices, 0, st, reinterpret_cast<const short*>(raw), bands_in, kHW, clip, out);
@@ -776,7 +777,7 @@ int dta_grad_allreduce(dta_ctx* ctx, int rank, int world, void* const peer_buffe
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
-  ctx->launches = 0;
+  ctx->launches_total += ctx->launches; ctx->launches = 0;
   pdl_enabled() = ctx->pdl;
   StageScope sc(ctx, "dist.grad_allreduce", st);
   // every CTA spins on flags, so the grid must be co-resident: far below one CTA per SM
@@ -803,7 +804,7 @@ int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, c
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
-  ctx->launches = 0;
+  ctx->launches_total += ctx->launches; ctx->launches = 0;
   pdl_enabled() = ctx->pdl;
   HeadPtrs h{};
   for (int i = 0; i < n_heads; ++i) {
@@ -839,7 +840,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
-  ctx->launches = 0;
+  ctx->launches_total += ctx->launches; ctx->launches = 0;
   pdl_enabled() = ctx->pdl;
 
   const int B = shape->batch, nb = d.nb, bands = shape->bands, classes = shape->classes;

@@ -19,7 +19,7 @@ inline int grid_for(size_t total, int sm_count) {
 int begin_call(dta_ctx* ctx) {
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
-  ctx->launches = 0;
+  ctx->launches_total += ctx->launches; ctx->launches = 0;
   return DTA_OK;
 }
 

@@ -19,7 +19,8 @@ struct dta_ctx {
   int device = 0;
   int sm_count = 0;
   int conv_impl = 1;   // 1: tcgen05 split-bf16 implicit GEMM (every convolution, forward / input gradient / weight gradient), 0: fp32 SIMT
-  long long launches = 0;
+  long long launches = 0;         // kernels launched by the current / last C-ABI call
+  long long launches_total = 0;   // ... by all earlier calls on this context (option "launches_total" = both)
   int profile = 0;
   int fuse_x = 1;      // conv1 forward converts the raw crops itself (no separate pack pass); 0 = pack kernel + pre-packed operand
   std::vector<std::string> stage_names;

@@ -57,6 +57,8 @@ def cross_entropy_heads(heads: Sequence[torch.Tensor], y: torch.Tensor, weight: 
         raise RuntimeError("deeptreeattention_b200 has no CPU path: scores must live on a CUDA (sm_100) device")
     if y.dtype != torch.int64 or y.dim() != 1 or y.shape[0] != heads[0].shape[0]:
         raise ValueError("labels must be int64 of shape (batch,)")
+    if y.device != heads[0].device or (weight is not None and weight.device != heads[0].device):
+        raise RuntimeError(f"labels / class weights must be on the scores' device ({heads[0].device})")
     for h in heads:
         if h.dtype != torch.float32 or h.shape != heads[0].shape or h.dim() != 2:
             raise ValueError("every head must be float32 of the same (batch, classes) shape")

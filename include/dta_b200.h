@@ -121,7 +121,8 @@ const char* dta_last_error(const dta_ctx* ctx); /* ctx may be NULL: last create 
 
 /* Tuning / debugging knobs.  key "conv_impl": 0 = fp32 CUDA-core direct convolution,
  * 1 = tcgen05 split-bf16 implicit GEMM (default where implemented).
- * key "launches": read-only counter of kernels launched by the last forward/backward.
+ * key "launches": read-only counter of kernels launched by the last C-ABI call; "launches_total": by every call on this
+ * context so far (difference of two reads = kernels of the calls in between).
  * key "profile": 1 = record per-stage CUDA-event timings (see dta_profile_read).
  * key "overlap": 2 (default) / 1 = work off the critical path (parameter packing, weight gradients, small reductions) runs on a
  * library-owned side stream, forked from and joined back to the caller's stream with events inside each call (still one

@@ -199,6 +199,16 @@ def make_inputs(batch: int, bands: int, classes: int, seed: int, dist: str = "un
 
 # --------------------------------------------------------------------------- forward
 Z_RECORD: Optional[Dict[str, torch.Tensor]] = None   # tests: set to a dict to collect every block's convolution output
+# tests / fixture screening: "split_bf16x3" evaluates every 3x3 convolution's VALUE in the arithmetic of the tensor-core kernels
+# (operands split v = hi + lo into two round-to-nearest bf16, products hi*hi + hi*lo + lo*hi, csrc/dta_tc.cuh split2) while
+# the derivative stays the exact one: shows which ReLU / max-pool decisions that arithmetic can move
+CONV_ARITH: Optional[str] = None
+
+
+def split_bf16(v: torch.Tensor):
+    hi = v.float().bfloat16().float()
+    lo = (v.float() - hi).bfloat16().float()
+    return hi.to(v.dtype), lo.to(v.dtype)
 
 
 def conv_block(p: Params, prefix: str, u: torch.Tensor, pool: bool, training: bool,
@@ -216,6 +226,13 @@ def conv_block(p: Params, prefix: str, u: torch.Tensor, pool: bool, training: bo
     piecewise-linear network (see tests/test_gpu_parity.py).
     """
     z = F.conv2d(u, p[f"{prefix}.conv_layer.weight"], p[f"{prefix}.conv_layer.bias"], padding=1)
+    if CONV_ARITH == "split_bf16x3":
+        with torch.no_grad():
+            uh, ul = split_bf16(u)
+            wh, wl = split_bf16(p[f"{prefix}.conv_layer.weight"])
+            z_em = (F.conv2d(uh, wh, p[f"{prefix}.conv_layer.bias"], padding=1) + F.conv2d(uh, wl, None, padding=1)
+                    + F.conv2d(ul, wh, None, padding=1))
+        z = z + (z_em - z).detach()
     if Z_RECORD is not None:
         Z_RECORD[prefix] = z.detach().clone()
     if z_values is not None and prefix in z_values:

@@ -17,7 +17,8 @@ defined away from kinks, so every case's seed is advanced until the reference's 
 stable (5e-4 relative) under three random 1e-5 relative perturbations of crops and weights
 (above the 2^-18 = 3.8e-6 operand rounding of the split-bf16 tensor-core convolutions, and far above
 the noise of an fp32 evaluation with a different summation order).  The accepted seed
-is recorded in cases.json and the measured per-tensor sensitivity is stored next to each
+is recorded in cases.json (the same stability is required between the exact evaluation and one whose
+convolution values are computed in the tensor-core kernels' split-bf16 arithmetic, oracle CONV_ARITH) and the measured per-tensor sensitivity is stored next to each
 gradient (``grad/<name>/sens``) so tests can widen the tolerance by the reference's own
 conditioning instead of guessing.
 
@@ -84,6 +85,15 @@ def kink_stable(ref, case, seed, eps=1e-5, tol=5e-4, draws=3):
     gen = torch.Generator().manual_seed(seed)
     sens = {k: 0.0 for k, g in base.items() if g is not None}
     stable = True
+    # the tensor-core kernels' own arithmetic (split-bf16 operands, three products) must not move a decision either
+    orc.CONV_ARITH = "split_bf16x3"
+    try:
+        g_tc = orc.step(kind, table, x, y, regime=regime, training=training)[3]
+    finally:
+        orc.CONV_ARITH = None
+    for k, g in base.items():
+        if g is not None and float((g - g_tc[k]).abs().max()) > tol * float(g.abs().max()) + 2e-6:
+            return False, {}
     for _ in range(draws):
         t2 = {k: (v * (1 + eps * torch.randn(v.shape, generator=gen, dtype=v.dtype))
                   if (v.is_floating_point() and not orc.is_buffer(k)) else v.clone()) for k, v in table.items()}
