@@ -152,7 +152,18 @@ class _FusedNetFunction(torch.autograd.Function):
             # every float gradient lives in ONE flat buffer (a single all-reduce covers it)
             numels = [p.numel() if p.dtype == torch.float32 else 0 for p in params]
             bufs = spec.grad_buffers
-            if bufs is not None and bufs[0].numel() == sum(numels) and bufs[0].device == dev:
+            persistent = bufs is not None and bufs[0].numel() == sum(numels) and bufs[0].device == dev
+            if persistent:
+                # A parameter whose .grad is STILL a view of the persistent buffer (gradient accumulation over micro-batches,
+                # zero_grad(set_to_none=False), two forwards feeding one backward) must not see that buffer wiped: this
+                # backward then writes into a temporary and autograd's AccumulateGrad adds it onto the live views.
+                lo, hi = bufs[0].data_ptr(), bufs[0].data_ptr() + bufs[0].numel() * 4
+                persistent = not any(p.grad is not None and (lo <= p.grad.data_ptr() < hi or p.grad.data_ptr() == bufs[1].data_ptr())
+                                     for p in params)
+                accumulating = not persistent
+            else:
+                accumulating = False
+            if persistent:
                 flat, galpha = bufs
                 flat.zero_()
                 galpha.zero_()
@@ -173,7 +184,8 @@ class _FusedNetFunction(torch.autograd.Function):
                                   djoint.data_ptr() if djoint is not None else None, C.byref(gtable), None,
                                   work.data_ptr(), _stream_ptr(dev))
         _capi.check(handle, rc, "dta_backward")
-        spec.flat_grad, spec.alpha_grad = flat, (galpha if djoint is not None else None)
+        if not accumulating:     # (accumulating: the sums live on in the persistent buffer spec.flat_grad already names)
+            spec.flat_grad, spec.alpha_grad = flat, (galpha if djoint is not None else None)
         out = []
         for name, g, need in zip(ctx.names, grads, ctx.needs_input_grad[5:]):
             if not need:
@@ -204,9 +216,13 @@ class _FusedNet(Module):
         if x.dim() != 4 or x.shape[1] != self._bands or x.shape[2] != 11 or x.shape[3] != 11:
             raise ValueError(f"expected crops of shape (B, {self._bands}, 11, 11), got {tuple(x.shape)}")
         x = x.contiguous()
+        # the cached name/tensor lists are valid only while every parameter and buffer OBJECT is the one they were built
+        # from: swapping a head (net.classifier3 = Classifier(...)), a sub-network or a single tensor must be picked up like
+        # the reference nn.Module does
+        ident = tuple(map(id, self.parameters())) + tuple(map(id, self.buffers()))
         cache = self.__dict__.get("_fused_cache")
-        if cache is not None and (next(self.buffers()) is not cache[4] or next(self.parameters()) is not cache[1][0]):
-            cache = None                                # a sub-module was moved/replaced on its own
+        if cache is not None and cache[4] != ident:
+            cache = None
         if cache is None:
             names, params, buffers = [], [], {}
             for k, v in self.state_dict(keep_vars=True).items():
@@ -215,7 +231,13 @@ class _FusedNet(Module):
                     params.append(v)
                 else:
                     buffers[k] = v
-            cache = (names, params, buffers, _NetSpec(self._net_kind, self._bands, self._classes), next(self.buffers()))
+            # the class count is whatever the last head says now (a swapped head may have changed it)
+            head = [v for k, v in zip(names, params) if k.endswith("fc1.weight")][-1]
+            heads = [v.shape[0] for k, v in zip(names, params) if k.endswith("fc1.weight")]
+            if any(h != head.shape[0] for h in heads):
+                raise ValueError(f"every classifier head must have the same number of classes, got {heads}")
+            self._classes = int(head.shape[0])
+            cache = (names, params, buffers, _NetSpec(self._net_kind, self._bands, self._classes), ident)
             self.__dict__["_fused_cache"] = cache
         names, params, buffers, spec = cache[:4]
         spec.grad_buffers = self.__dict__.get("_grad_buffers")
@@ -230,6 +252,14 @@ class _FusedNet(Module):
     def load_state_dict(self, *args, **kwargs):
         self.__dict__.pop("_fused_cache", None)
         return super().load_state_dict(*args, **kwargs)
+
+    def __getstate__(self):
+        """copy.deepcopy / pickle / torch.save(model): the call cache (ctypes pointer tables, flat gradient views) and the
+        symmetric-memory gradient buffers belong to THIS object on THIS device and are rebuilt on the first call."""
+        state = self.__dict__.copy()
+        state.pop("_fused_cache", None)
+        state.pop("_grad_buffers", None)
+        return state
 
     def fused_spec(self):
         """Spec of the last fused call (holds the flat gradient buffer after a backward)."""

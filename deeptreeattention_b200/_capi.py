@@ -152,7 +152,7 @@ def lib():
         L.dta_profile_read.restype = C.c_int
         L.dta_query_sizes.argtypes = [C.POINTER(Shape), C.POINTER(Sizes)]
         L.dta_query_sizes.restype = C.c_int
-        L.dta_saved_region.argtypes = [C.POINTER(Shape), C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.dta_saved_region.argtypes = [C.POINTER(Shape), C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.dta_saved_region.restype = C.c_int
         L.dta_forward.argtypes = [C.c_void_p, C.POINTER(Shape), C.c_void_p, C.POINTER(Tensors),
                                   C.POINTER(C.c_void_p * 6), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -239,11 +239,12 @@ def query_sizes(net_kind: int, batch: int, bands: int, classes: int, training: b
     return out
 
 
-def saved_region(net_kind: int, batch: int, bands: int, classes: int, training: bool, block: int):
-    """(byte offset, float count) of convolution block ``block``'s output inside a forward's ``saved`` buffer (diagnostic)."""
+def saved_region(net_kind: int, batch: int, bands: int, classes: int, training: bool, block: int, region: int = 0):
+    """(byte offset, float count) of convolution block ``block``'s output (region 0) / BatchNorm scale (1) / shift (2) inside a
+    forward's ``saved`` buffer (diagnostic)."""
     s = Shape(net_kind, batch, bands, classes, int(training))
     off, n = C.c_size_t(), C.c_size_t()
-    if lib().dta_saved_region(C.byref(s), block, C.byref(off), C.byref(n)) != DTA_OK:
+    if lib().dta_saved_region(C.byref(s), block, region, C.byref(off), C.byref(n)) != DTA_OK:
         raise ValueError("dta_saved_region rejected the shape / block")
     return off.value, n.value
 

@@ -511,14 +511,15 @@ int dta_query_sizes(const dta_shape* shape, dta_sizes* out) {
   return DTA_OK;
 }
 
-int dta_saved_region(const dta_shape* shape, int block, size_t* offset_bytes, size_t* n_floats) {
+int dta_saved_region(const dta_shape* shape, int block, int region, size_t* offset_bytes, size_t* n_floats) {
   NetDesc d;
   if (!shape || !offset_bytes || !n_floats || !describe(shape->net_kind, &d)) return DTA_ERR_INVALID_ARG;
-  if (shape->batch <= 0 || shape->bands <= 0 || shape->classes <= 0 || block < 0 || block > 2) return DTA_ERR_INVALID_ARG;
+  if (shape->batch <= 0 || shape->bands <= 0 || shape->classes <= 0 || block < 0 || block > 2 || region < 0 || region > 2) return DTA_ERR_INVALID_ARG;
   char* const base = reinterpret_cast<char*>(uintptr_t(256));   // any non-null base: only differences are used
   const SavedLayout L = layout_saved(*shape, d, base);
-  *offset_bytes = (size_t)(reinterpret_cast<char*>(L.z[block]) - base);
-  *n_floats = (size_t)shape->batch * d.nb * kC[block] * kHWpre[block];
+  const float* p = region == 0 ? L.z[block] : (region == 1 ? L.bn_scale[block] : L.bn_shift[block]);
+  *offset_bytes = (size_t)(reinterpret_cast<const char*>(p) - base);
+  *n_floats = region == 0 ? (size_t)shape->batch * d.nb * kC[block] * kHWpre[block] : (size_t)d.nb * kC[block];
   return DTA_OK;
 }
 

@@ -123,13 +123,13 @@ class metadata(Module):
         self.mlp = nn.Linear(in_features=16, out_features=classes)
         self.dropout = nn.Dropout(p=0.7)
 
-    def _buffers(self):
+    def _bn_buffers(self):
         bn = self.batch_norm
         return {"bn_rm": bn.running_mean, "bn_rv": bn.running_var, "bn_nbt": bn.num_batches_tracked}
 
     def forward(self, x, keep_mask=None):
         site = _check_inputs(x, self.embedding.weight)
-        return _MetadataFunction.apply(site, None, self.training, self.embedding.num_embeddings, self._buffers(),
+        return _MetadataFunction.apply(site, None, self.training, self.embedding.num_embeddings, self._bn_buffers(),
                                        _keep(keep_mask, site.shape[0], site.device), _draw_seed() if (self.training and keep_mask is None) else 0,
                                        self.embedding.weight, self.batch_norm.weight, self.batch_norm.bias, self.mlp.weight,
                                        self.mlp.bias, None, None)
@@ -150,7 +150,7 @@ class metadata_sensor_fusion(Module):
         sensor_softmax = self.sensor_model(images)          # the reference's name; these are the joint scores (:39)
         if site.shape[0] != sensor_softmax.shape[0]:
             raise ValueError("images and metadata must have the same batch size")
-        return _MetadataFunction.apply(site, sensor_softmax, self.training, mm.embedding.num_embeddings, mm._buffers(),
+        return _MetadataFunction.apply(site, sensor_softmax, self.training, mm.embedding.num_embeddings, mm._bn_buffers(),
                                        _keep(keep_mask, site.shape[0], site.device), _draw_seed() if (self.training and keep_mask is None) else 0,
                                        mm.embedding.weight, mm.batch_norm.weight, mm.batch_norm.bias, mm.mlp.weight, mm.mlp.bias,
                                        self.fc1.weight, self.fc1.bias)

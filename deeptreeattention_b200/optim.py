@@ -83,6 +83,20 @@ class FusedAdam(torch.optim.Optimizer):
             if st is not None and st["lr_dev"] is not None:
                 st["lr_dev"].fill_(float(group["lr"]))
 
+    def state_dict(self):
+        """torch-Adam-shaped checkpoint.  In capturable mode the step that counts is the DEVICE counter (it advances on every
+        CUDA-graph replay, the host-side ``state[p]["step"]`` only when Python runs ``step()``): it is read back here so a
+        resumed run continues the bias correction where the saved one stopped."""
+        for gi, group in enumerate(self.param_groups):
+            st = self._flat.get(gi)
+            if st is None or st["step_dev"] is None:
+                continue
+            step = int(st["step_dev"].item())
+            for p in group["params"]:
+                if p in self.state and "step" in self.state[p]:
+                    self.state[p]["step"] = step
+        return super().state_dict()
+
     def load_state_dict(self, state_dict):
         """Loads a torch-Adam-shaped checkpoint: the moments are copied INTO the flat buffers (views stay views)."""
         super().load_state_dict(state_dict)

@@ -150,12 +150,15 @@ int dta_profile_read(dta_ctx* ctx, dta_stage_time* out, int capacity, int* count
 /* Pure host arithmetic: buffer sizes for a shape (no GPU needed). */
 int dta_query_sizes(const dta_shape* shape, dta_sizes* out);
 
-/* Pure host arithmetic: where inside `saved` the forward leaves convolution block `block`'s (0..2) output z -- the
- * pre-BatchNorm value of conv_module.forward (Hang2020.py:25), bias included -- as NCHW float32
- * (batch, branches * C_block, S, S), branch-major on the channel axis (spectral then spatial for HANG2020), S = 11, 11, 5.
+/* Pure host arithmetic: where inside `saved` the forward leaves, for convolution block `block` (0..2),
+ *   region 0: the convolution output z -- the pre-BatchNorm value of conv_module.forward (Hang2020.py:25), bias included --
+ *             as NCHW float32 (batch, branches * C_block, S, S), branch-major on the channel axis (spectral then spatial for
+ *             HANG2020), S = 11, 11, 5;
+ *   region 1 / 2: the per-channel BatchNorm scale = gamma * invstd and shift = beta - mean * scale (branches * C_block floats
+ *             each) every kernel applies as a = fmaf(z, scale, shift).
  * Diagnostic view for parity tests (they hand these values to the float64 oracle so that both sides take every ReLU /
  * max-pool decision on the same numbers); nothing on the product path calls it. */
-int dta_saved_region(const dta_shape* shape, int block, size_t* offset_bytes, size_t* n_floats);
+int dta_saved_region(const dta_shape* shape, int block, int region, size_t* offset_bytes, size_t* n_floats);
 
 /*
  * Forward.  Replaces Hang2020.forward / spectral_network.forward / spatial_network.forward /

@@ -223,7 +223,9 @@ def conv_block(p: Params, prefix: str, u: torch.Tensor, pool: bool, training: bo
     block then continues from THOSE values while gradients still flow through this oracle's own convolution
     (value substitution, derivative unchanged): every ReLU / max-pool decision downstream is taken on the same
     numbers as in the implementation under test, which is what makes a gradient comparison well defined for a
-    piecewise-linear network (see tests/test_gpu_parity.py).
+    piecewise-linear network (see tests/test_gpu_parity.py).  ``z_values["bn:" + prefix]``: likewise the values AFTER
+    BatchNorm, i.e. the numbers whose sign the ReLU tests (an implementation that normalises as fmaf(z, scale, shift) in
+    float32 can disagree with a float64 BatchNorm about the sign of an activation that is 1e-8 from zero).
     """
     z = F.conv2d(u, p[f"{prefix}.conv_layer.weight"], p[f"{prefix}.conv_layer.bias"], padding=1)
     if CONV_ARITH == "split_bf16x3":
@@ -242,6 +244,8 @@ def conv_block(p: Params, prefix: str, u: torch.Tensor, pool: bool, training: bo
                      training=training, momentum=BN_MOMENTUM, eps=BN_EPS)
     if training:
         p[f"{prefix}.bn1.num_batches_tracked"] += 1
+    if z_values is not None and ("bn:" + prefix) in z_values:      # the other implementation's post-BatchNorm values (see above)
+        a = a + (z_values["bn:" + prefix].to(a.dtype) - a).detach()
     r = F.relu(a)
     if pool:
         r = F.max_pool2d(r, (2, 2))

@@ -110,26 +110,33 @@ _KIND_ID = {"hang2020": 0, "spectral": 1, "spatial": 2, "vanilla": 3}
 
 
 def cuda_conv_outputs(model, kind, batch, bands, classes, training):
-    """``{oracle block prefix: z}``: the three convolution outputs (pre-BatchNorm, bias included) the CUDA forward just left
-    in its ``saved`` buffer (``dta_saved_region``; needs ``_capi.KEEP_SAVED``), split per branch, on the CPU."""
+    """``{oracle block prefix: z, "bn:" + prefix: a}``: the three convolution outputs z (pre-BatchNorm, bias included) the CUDA
+    forward just left in its ``saved`` buffer and the post-BatchNorm values a = fmaf(z, scale, shift) every kernel derives from
+    them (scale / shift read from the same buffer; the fused multiply-add is reproduced exactly: float32 product and sum are
+    exact in float64, then ONE rounding).  ``dta_saved_region``; needs ``_capi.KEEP_SAVED``.  Split per branch, on the CPU."""
     from deeptreeattention_b200 import _capi
     saved = model.fused_spec().last_saved
     assert saved is not None, "set _capi.KEEP_SAVED before the forward"
     out = {}
     nb = 2 if kind == "hang2020" else 1
+
+    def region(blk, which):
+        off, n = _capi.saved_region(_KIND_ID[kind], batch, bands, classes, training, blk, which)
+        return saved[off:off + 4 * n].view(torch.float32).cpu()
+
     for blk, (c, s) in enumerate(((32, 11), (64, 11), (128, 5))):
-        off, n = _capi.saved_region(_KIND_ID[kind], batch, bands, classes, training, blk)
-        z = saved[off:off + 4 * n].view(torch.float32).view(batch, nb * c, s, s).cpu()
-        if kind == "hang2020":
-            out[f"spectral_network.conv{blk + 1}"] = z[:, :c].contiguous()
-            out[f"spatial_network.conv{blk + 1}"] = z[:, c:].contiguous()
-        else:
-            out[f"conv{blk + 1}"] = z
+        z = region(blk, 0).view(batch, nb * c, s, s)
+        scale, shift = region(blk, 1).double().view(1, -1, 1, 1), region(blk, 2).double().view(1, -1, 1, 1)
+        a = (z.double() * scale + shift).float()
+        names = [f"spectral_network.conv{blk + 1}", f"spatial_network.conv{blk + 1}"] if kind == "hang2020" else [f"conv{blk + 1}"]
+        for g, name in enumerate(names):
+            out[name] = z[:, g * c:(g + 1) * c].contiguous()
+            out["bn:" + name] = a[:, g * c:(g + 1) * c].contiguous()
     return out
 
 
 def matched_oracle_step_fp64(kind, table, x, y, regime, training, z_values):
-    """The float64 oracle continued from the convolution outputs of the implementation under test (value substitution only;
+    """The float64 oracle continued from the convolution outputs (and their BatchNorm images) of the implementation under test (value substitution only;
     every derivative is the oracle's own).  A Hang2020 network is piecewise linear in its activations: its gradient is only
     comparable between two evaluations that sit on the same linear piece, i.e. take the same ReLU / max-pool decisions.
     Forward parity (scores against the UNMATCHED oracle) bounds how far the substituted values are from the oracle's own."""

@@ -8,8 +8,9 @@ the reference top-2 margin exceeds 1e-4; BatchNorm running statistics 1e-5.  Gra
    rounding distance of a ReLU threshold falls on either side depending on the arithmetic (split-bf16 operands carry
    2^-18 relative rounding, fp32 2^-24), and ONE such flip among a million activations moves a weight-gradient tensor by
    ~1e-3 in L2 -- in any implementation, the reference's cuDNN path included.  So the oracle is continued from the CUDA
-   path's own convolution outputs (``dta_saved_region`` -> ``conv_block(z_values=...)``: values substituted, derivatives
-   the oracle's): both sides then take every decision on the same numbers and the comparison measures the backward kernels,
+   path's own convolution outputs and their BatchNorm images a = fmaf(z, scale, shift) (``dta_saved_region`` ->
+   ``conv_block(z_values=...)``: values substituted, derivatives the oracle's): both sides then take every decision on the
+   same numbers and the comparison measures the backward kernels,
    not the luck of the roundings.  How far those convolution outputs are from the oracle's own is bounded separately by the
    forward checks (scores against the unmatched float64 oracle: <= 2e-4 at the benchmark shapes);
  * conv biases under batch-statistics BatchNorm have true gradient 0: absolute 1e-5."""
@@ -46,6 +47,10 @@ def assert_grads_l2(kind, table, x, y, regime, training, grads, zvals, label="",
             assert float(g.abs().max()) <= 1e-7, k
             continue
         err = gu.rel_l2(g, rg)
+        if rg.numel() == 1 and k.endswith(".bias") and k[:-4] + "weight" in g64:
+            # a one-element bias gradient is a batch sum with cancellation (|sum| can be 1e-4 of the sum of |terms|): hold its
+            # ABSOLUTE error to the scale of the sibling weight gradient, which sums the same terms
+            err = float((g.double() - rg).abs().max() / max(float(rg.abs().max()), float(g64[k[:-4] + "weight"].double().norm())))
         if report is not None:
             report[k] = err
         if err > L2_TOL:
@@ -358,7 +363,7 @@ def test_gradient_l2_parity_vs_fp64_oracle(kind, bands, classes, batch, label):
         assert_argmax(h, rh.detach().float().numpy())
     for k, rb in rbufs.items():
         np.testing.assert_allclose(bufs[k].numpy(), rb.numpy(), rtol=1e-5, atol=1e-5)
-    zdiff = max(float((z_tc[k] - z_simt[k]).abs().max() / z_simt[k].abs().max()) for k in z_tc)
+    zdiff = max(float((z_tc[k] - z_simt[k]).abs().max() / z_simt[k].abs().max()) for k in z_tc if not k.startswith("bn:"))
     assert zdiff <= 3e-5, f"convolution outputs of the two CUDA paths differ by {zdiff:.2e} of their range"
     m_tc, m_simt = {}, {}
     fail = None

@@ -87,14 +87,20 @@ def test_cuda_module_drops_into_treemodel():
     assert abs(tm.logged["val_loss"][0] - tm_ref.logged["val_loss"][0]) < 2e-3  # eval mode: running statistics after 5 updates
     assert tm.optimizer.param_groups[0]["lr"] == tm_ref.optimizer.param_groups[0]["lr"]
 
-    # trained parameters agree (Adam moves every element by ~lr per step whatever the gradient's size, so elements whose true
-    # gradient is rounding noise -- conv biases under batch statistics -- are compared on what they do, below, not here)
+    # trained parameters: Adam moves EVERY element by ~lr per step whatever the size of its gradient, so an element whose
+    # gradient is rounding noise can walk the other way (that is the reference's behaviour on another machine, too); what is
+    # comparable is the update as a whole: relative L2 of (trained - initial) per tensor
     tr = ref.table() if kind == "port" else dict(ref.state_dict())
     for k, v in ours.state_dict().items():
         if orc.is_buffer(k) or k.endswith("conv_layer.bias"):
             continue
-        d = float((v.detach().cpu().double() - tr[k].detach().double()).abs().max())
-        assert d <= 2.5e-4, f"{k}: trained parameter differs by {d:.2e}"
+        du = v.detach().cpu().double() - table[k].double()
+        dr = tr[k].detach().double() - table[k].double()
+        if float(dr.norm()) == 0.0:
+            assert float(du.norm()) == 0.0, k
+            continue
+        rel = float((du - dr).norm() / dr.norm())
+        assert rel <= 5e-2, f"{k}: update differs by {rel:.2e} (relative L2)"
 
     # state_dict round trip: the reference-trained weights load into the CUDA module and predict alike
     state = {k: v.detach().clone() for k, v in tr.items()}
