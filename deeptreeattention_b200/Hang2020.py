@@ -259,6 +259,7 @@ class _FusedNet(Module):
         state = self.__dict__.copy()
         state.pop("_fused_cache", None)
         state.pop("_grad_buffers", None)
+        state.pop("head_scores", None)     # last call's outputs (autograd graph attached): not part of the module's state
         return state
 
     def fused_spec(self):

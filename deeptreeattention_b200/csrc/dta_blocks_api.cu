@@ -435,25 +435,34 @@ int dta_metadata_backward(dta_ctx* ctx, int batch, int sites, int classes, int t
   cudaFuncSetAttribute(meta_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   meta_bwd_rows_kernel<<<(batch + kMetaCrops - 1) / kMetaCrops, kMetaThreads, smem, st>>>(sidx, batch, sites, C, fused, p, sv, out, dout, wk, dsensor);
   DTA_CHECK_LAUNCH(ctx, "meta_bwd_rows");
+  // every batch reduction in one launch (fixed order): fusion weights / bias, site-MLP weights / bias, BatchNorm1d sums
+  MetaReduceTable tab{};
+  int tiles = 0;
+  auto add = [&](const float* U, int ldu, const float* V, int ldv, int ni, int nj, float* out, int si, int sj) {
+    if (!out) return;
+    MetaReduceTask& t = tab.t[tab.n++];
+    t.U = U; t.V = V; t.out = out; t.ldu = ldu; t.ldv = ldv; t.si = si; t.sj = sj; t.ni = ni; t.nj = nj;
+    t.tile_begin = tiles; t.tiles_j = V ? (nj + 31) / 32 : 1;
+    tiles += V ? ((ni + 31) / 32) * t.tiles_j : (ni + 31) / 32;
+  };
   if (fused) {
     // dfc_w[i][j] = sum_b U1[b][i] * cat[b][j], cat = [m | sensor]
-    if (grads->fc_w) {
-      batch_sum(ctx, st, wk.u1, C, sv.m, C, batch, C, C, grads->fc_w, 2 * (size_t)C, 1);
-      batch_sum(ctx, st, wk.u1, C, sensor, C, batch, C, C, grads->fc_w + C, 2 * (size_t)C, 1);
-    }
-    batch_sum(ctx, st, wk.u1, C, nullptr, 0, batch, C, 1, grads->fc_b, 1, 0);
+    add(wk.u1, C, sv.m, C, C, C, grads->fc_w, 2 * C, 1);
+    add(wk.u1, C, sensor, C, C, C, grads->fc_w ? grads->fc_w + C : nullptr, 2 * C, 1);
+    add(wk.u1, C, nullptr, 0, C, 1, grads->fc_b, 1, 0);
   }
-  batch_sum(ctx, st, wk.u2, C, sv.d, kMetaDim, batch, C, kMetaDim, grads->mlp_w, kMetaDim, 1);
-  batch_sum(ctx, st, wk.u2, C, nullptr, 0, batch, C, 1, grads->mlp_b, 1, 0);
-  batch_sum(ctx, st, wk.dyx, kMetaDim, nullptr, 0, batch, kMetaDim, 1, wk.dgamma, 1, 0);
-  batch_sum(ctx, st, wk.dy, kMetaDim, nullptr, 0, batch, kMetaDim, 1, wk.dbeta, 1, 0);
+  add(wk.u2, C, sv.d, kMetaDim, C, kMetaDim, grads->mlp_w, kMetaDim, 1);
+  add(wk.u2, C, nullptr, 0, C, 1, grads->mlp_b, 1, 0);
+  add(wk.dyx, kMetaDim, nullptr, 0, kMetaDim, 1, wk.dgamma, 1, 0);
+  add(wk.dy, kMetaDim, nullptr, 0, kMetaDim, 1, wk.dbeta, 1, 0);
+  meta_reduce_kernel<<<tiles, 256, 0, st>>>(tab, batch);
+  DTA_CHECK_LAUNCH(ctx, "meta_reduce");
   if (grads->bn_w || grads->bn_b) {
     meta_copy16_kernel<<<1, 32, 0, st>>>(wk.dgamma, grads->bn_w, wk.dbeta, grads->bn_b);
     DTA_CHECK_LAUNCH(ctx, "meta_copy16");
   }
   if (grads->embedding) {
-    const int total = sites * kMetaDim;
-    meta_bwd_embed_kernel<<<(total + 127) / 128, 128, 0, st>>>(sidx, batch, sites, p, sv, wk, training, grads->embedding);
+    meta_bwd_embed_kernel<<<sites, 256, 0, st>>>(sidx, batch, sites, p, sv, wk, training, grads->embedding);
     DTA_CHECK_LAUNCH(ctx, "meta_bwd_embed");
   }
   cudaError_t e = cudaGetLastError();

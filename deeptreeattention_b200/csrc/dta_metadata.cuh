@@ -235,23 +235,95 @@ meta_bwd_rows_kernel(const long long* __restrict__ site, int B, int sites, int C
   }
 }
 
-// Embedding gradient through the BatchNorm1d backward (one thread per table element, batch walked in order):
+// Embedding gradient through the BatchNorm1d backward (one CTA per site: 16 features x 16 batch slices, slices added in order):
 //   train: dx = gamma*istd * (dy - dbeta/B - xhat*dgamma/B) ; eval: dx = gamma*istd*dy ;  dE[s][f] = sum_{b: site[b]=s} dx[b][f]
-__global__ void meta_bwd_embed_kernel(const long long* __restrict__ site, int B, int sites, MetaTensors p, MetaSaved sv, MetaWork wk,
-                                      int training, float* __restrict__ demb) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= sites * kMetaDim) return;
-  const int s = idx / kMetaDim, f = idx - s * kMetaDim;
+__global__ void __launch_bounds__(256)
+meta_bwd_embed_kernel(const long long* __restrict__ site, int B, int sites, MetaTensors p, MetaSaved sv, MetaWork wk,
+                      int training, float* __restrict__ demb) {
+  __shared__ float part[16][kMetaDim];
+  const int s = blockIdx.x, f = threadIdx.x & (kMetaDim - 1), slice = threadIdx.x / kMetaDim;
   const float k0 = p.bn_w[f] * sv.istd[f];
   const float xhat = (p.emb[(size_t)s * kMetaDim + f] - sv.mean[f]) * sv.istd[f];
   const float c1 = training ? wk.dbeta[f] / (float)B : 0.f, c2 = training ? xhat * wk.dgamma[f] / (float)B : 0.f;
   float acc = 0.f;
-  for (int b = 0; b < B; ++b) {
+  for (int b = slice; b < B; b += 16) {
     long long sidx = site[b];
     sidx = sidx < 0 ? 0 : (sidx >= sites ? sites - 1 : sidx);
     if (sidx == s) acc += k0 * (wk.dy[(size_t)b * kMetaDim + f] - c1 - c2);
   }
-  demb[idx] = acc;
+  part[slice][f] = acc;
+  __syncthreads();
+  if (slice == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) t += part[k][f];
+    demb[(size_t)s * kMetaDim + f] = t;
+  }
+}
+
+// All batch reductions of the backward in ONE launch: task t computes out[i*si + j*sj] = sum_b U[b*ldu + i] * V[b*ldv + j]
+// (V == nullptr: column sums of U).  A CTA owns one 32x32 output tile of one task and walks the whole batch in order
+// (fixed summation order, no atomics); 256 threads, 2x2 outputs each.
+struct MetaReduceTask {
+  const float* U; const float* V; float* out;
+  int ldu, ldv, si, sj, ni, nj, tile_begin, tiles_j;
+};
+constexpr int kMetaMaxTasks = 8;
+struct MetaReduceTable {
+  MetaReduceTask t[kMetaMaxTasks];
+  int n;
+};
+__global__ void __launch_bounds__(256) meta_reduce_kernel(const __grid_constant__ MetaReduceTable tab, int B) {
+  __shared__ float su[32][33];
+  __shared__ float sv[32][33];
+  int ti = 0;
+  while (ti + 1 < tab.n && tab.t[ti + 1].tile_begin <= (int)blockIdx.x) ++ti;
+  const MetaReduceTask& T = tab.t[ti];
+  const int tile = blockIdx.x - T.tile_begin;
+  const int tid = threadIdx.x;
+  if (T.V == nullptr) {
+    const int tx = tid & 31, ty = tid >> 5;
+    const int i = tile * 32 + tx;
+    float a = 0.f;
+    if (i < T.ni)
+      for (int b = ty; b < B; b += 8) a += T.U[(size_t)b * T.ldu + i];
+    su[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && i < T.ni) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += su[k][tx];
+      T.out[(size_t)i * T.si] = t;
+    }
+    return;
+  }
+  const int i0 = (tile / T.tiles_j) * 32, j0 = (tile % T.tiles_j) * 32;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int b0 = 0; b0 < B; b0 += 32) {
+    for (int e = tid; e < 32 * 32; e += 256) {
+      const int bb = e >> 5, k = e & 31;
+      const int b = b0 + bb;
+      su[bb][k] = (b < B && i0 + k < T.ni) ? T.U[(size_t)b * T.ldu + i0 + k] : 0.f;
+      sv[bb][k] = (b < B && j0 + k < T.nj) ? T.V[(size_t)b * T.ldv + j0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int bb = 0; bb < 32; ++bb) {
+      const float u0 = su[bb][2 * ty], u1 = su[bb][2 * ty + 1];
+      const float v0 = sv[bb][2 * tx], v1 = sv[bb][2 * tx + 1];
+      acc[0][0] = fmaf(u0, v0, acc[0][0]); acc[0][1] = fmaf(u0, v1, acc[0][1]);
+      acc[1][0] = fmaf(u1, v0, acc[1][0]); acc[1][1] = fmaf(u1, v1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int i = i0 + 2 * ty + a, j = j0 + 2 * tx + c;
+      if (i < T.ni && j < T.nj) T.out[(size_t)i * T.si + (size_t)j * T.sj] = acc[a][c];
+    }
 }
 
 __global__ void meta_copy16_kernel(const float* __restrict__ a, float* __restrict__ da, const float* __restrict__ b, float* __restrict__ db) {

@@ -76,6 +76,19 @@ def rel_l2(a, b) -> float:
     return float((a - b).norm() / b.norm().clamp_min(1e-300))
 
 
+def grad_error(name, g, ref, all_refs) -> float:
+    """Relative L2 error of one gradient tensor -- except for a ONE-element bias gradient, which is a batch sum with
+    cancellation (|sum| can be 1e-4 of the sum of |terms|): its ABSOLUTE error is held to the scale of the sibling weight
+    gradient, which sums the same terms."""
+    ref = torch.as_tensor(ref)
+    g = torch.as_tensor(g)
+    sib = name[:-4] + "weight"
+    if ref.numel() == 1 and name.endswith(".bias") and all_refs.get(sib) is not None:
+        den = max(float(ref.double().abs().max()), float(torch.as_tensor(all_refs[sib]).double().norm()))
+        return float((g.double().reshape(-1) - ref.double().reshape(-1)).abs().max() / max(den, 1e-300))
+    return rel_l2(g, ref)
+
+
 def to_fp64(table):
     return {k: (v.double() if v.is_floating_point() else v.clone()) for k, v in table.items()}
 

@@ -46,11 +46,7 @@ def assert_grads_l2(kind, table, x, y, regime, training, grads, zvals, label="",
         if float(rg.abs().max()) == 0.0:      # dead gate in the oracle too
             assert float(g.abs().max()) <= 1e-7, k
             continue
-        err = gu.rel_l2(g, rg)
-        if rg.numel() == 1 and k.endswith(".bias") and k[:-4] + "weight" in g64:
-            # a one-element bias gradient is a batch sum with cancellation (|sum| can be 1e-4 of the sum of |terms|): hold its
-            # ABSOLUTE error to the scale of the sibling weight gradient, which sums the same terms
-            err = float((g.double() - rg).abs().max() / max(float(rg.abs().max()), float(g64[k[:-4] + "weight"].double().norm())))
+        err = gu.grad_error(k, g, rg, g64)
         if report is not None:
             report[k] = err
         if err > L2_TOL:

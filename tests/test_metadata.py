@@ -93,6 +93,8 @@ def test_cuda_matches_reference_golden(case):
     loss.backward()
     torch.cuda.synchronize()
     tol = 1e-3 if case["fused"] else 1e-5        # the fused output sits behind the sensor model's convolutions
+    if case["sites"] == 1 and case["training"]:
+        tol = max(tol, 1e-4)   # one site: BatchNorm1d sees identical rows, variance 0, invstd = 316 amplifies the rounding of (x - mean)
     np.testing.assert_allclose(out.detach().cpu().numpy(), gold["out"], rtol=0, atol=tol)
     assert abs(float(loss) - float(gold["loss"])) < tol
     sd = m.state_dict()
@@ -129,7 +131,7 @@ def test_cuda_matches_reference_golden(case):
             if float(rg.abs().max()) == 0.0:
                 assert float(grads[k].abs().max()) <= 1e-7, k
                 continue
-            assert gu.rel_l2(grads[k], rg) <= 1e-3, f"{k}: rel-L2 {gu.rel_l2(grads[k], rg):.3e}"
+            assert gu.grad_error(k, grads[k], rg, g64) <= 1e-3, f"{k}: rel-L2 {gu.grad_error(k, grads[k], rg, g64):.3e}"
 
 
 @pytest.mark.gpu
