@@ -88,7 +88,8 @@ def test_swapped_submodules_are_picked_up():
     w_blend = torch.sigmoid(torch.tensor(-0.3, dtype=torch.float64))
     heads = m.head_scores
     np.testing.assert_allclose(out.detach().cpu().numpy(),
-                               (heads[2].cpu().double() * w_blend + heads[5].cpu().double() * (1 - w_blend)).float().numpy(), atol=1e-5, rtol=0)
+                               (heads[2].detach().cpu().double() * w_blend + heads[5].detach().cpu().double() * (1 - w_blend)).float().numpy(),
+                               atol=1e-5, rtol=0)
     # 3. a different class count in one head only is an error, in all heads it is the new class count
     m.spatial_network.classifier3 = H.Classifier(in_features=512, classes=9).cuda()
     with pytest.raises(ValueError):
