@@ -233,6 +233,8 @@ BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
   return W;
 }
 
+inline bool tc_enabled_for_exchange(const dta_ctx* ctx) { return ctx->ex_mc != nullptr && ctx->ex_sync != nullptr; }
+
 int check_shape(dta_ctx* ctx, const dta_shape* s, NetDesc* d) {
   if (!ctx) return DTA_ERR_INVALID_ARG;
   if (!s) return fail(ctx, DTA_ERR_INVALID_ARG, "shape is NULL");
@@ -497,6 +499,7 @@ int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value) {
   if (!strcmp(key, "overlap")) { *value = ctx->overlap; return DTA_OK; }
   if (!strcmp(key, "pdl")) { *value = ctx->pdl; return DTA_OK; }
   if (!strcmp(key, "fuse_x")) { *value = ctx->fuse_x; return DTA_OK; }
+  if (!strcmp(key, "exchanged")) { *value = ctx->exchanged; return DTA_OK; }
   return DTA_ERR_INVALID_ARG;
 }
 
@@ -765,29 +768,54 @@ int dta_grad_allreduce_sizes(size_t n_float4, size_t n_double, int world, size_t
   return DTA_OK;
 }
 
+static int launch_allreduce(dta_ctx* ctx, cudaStream_t st, int rank, int world, void* const peer_buffers[], const void* mc, size_t n4, size_t nd,
+                            void* scratch, void* sync_words, const ArRanges& rg, int flag_set) {
+  PeerPtrs pp{};
+  for (int r = 0; r < world; ++r) pp.buf[r] = static_cast<float*>(peer_buffers[r]);
+  // every CTA spins on flags, so the grid must be co-resident: far below one CTA per SM
+  size_t work = n4;
+  if (mc != nullptr) {     // NVLS path: a rank only touches its own slice
+    if (rg.n > 0) { work = 0; for (int k = 0; k < rg.n; ++k) work += rg.hi[k] - rg.lo[k]; }
+    work = (work + world - 1) / world;
+  }
+  int grid = (int)((work + kArThreads - 1) / kArThreads);
+  if (grid > 64) grid = 64;
+  if (grid < 1) grid = 1;
+  grad_allreduce_kernel<<<grid, kArThreads, 0, st>>>(pp, static_cast<const float*>(mc), rank, world, n4, nd, static_cast<float*>(scratch),
+                                                     static_cast<uint32_t*>(sync_words), rg, flag_set);
+  DTA_CHECK_LAUNCH(ctx, "grad_allreduce");
+  return DTA_OK;
+}
+
 int dta_grad_allreduce(dta_ctx* ctx, int rank, int world, void* const peer_buffers[], const void* multicast_buffer, size_t n_float4,
                        size_t n_double, void* scratch, void* sync_words, void* cuda_stream) {
   if (!ctx) return DTA_ERR_INVALID_ARG;
   if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) return fail(ctx, DTA_ERR_INVALID_ARG, "need 0 <= rank < world <= 16");
   if (!peer_buffers || !scratch || !sync_words) return fail(ctx, DTA_ERR_INVALID_ARG, "peer_buffers, scratch and sync_words are required");
-  PeerPtrs pp{};
-  for (int r = 0; r < world; ++r) {
+  for (int r = 0; r < world; ++r)
     if (!peer_buffers[r]) return fail(ctx, DTA_ERR_INVALID_ARG, "peer_buffers[r] is NULL");
-    pp.buf[r] = static_cast<float*>(peer_buffers[r]);
-  }
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
   ctx->launches_total += ctx->launches; ctx->launches = 0;
   pdl_enabled() = ctx->pdl;
   StageScope sc(ctx, "dist.grad_allreduce", st);
-  // every CTA spins on flags, so the grid must be co-resident: far below one CTA per SM
-  int grid = (int)((n_float4 + kArThreads - 1) / kArThreads);
-  if (grid > 64) grid = 64;
-  if (grid < 1) grid = 1;
-  grad_allreduce_kernel<<<grid, kArThreads, 0, st>>>(pp, static_cast<const float*>(multicast_buffer), rank, world, n_float4, n_double,
-                                                     static_cast<float*>(scratch), static_cast<uint32_t*>(sync_words));
-  DTA_CHECK_LAUNCH(ctx, "grad_allreduce");
+  return launch_allreduce(ctx, st, rank, world, peer_buffers, multicast_buffer, n_float4, n_double, scratch, sync_words, ArRanges{}, 0);
+}
+
+int dta_set_grad_exchange(dta_ctx* ctx, int rank, int world, void* const peer_buffers[], const void* multicast_buffer, size_t n_float4,
+                          size_t n_double, void* sync_words) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  ctx->ex_world = 0;
+  ctx->exchanged = 0;
+  if (world <= 1 || !peer_buffers) return DTA_OK;
+  if (world > kMaxPeers || rank < 0 || rank >= world) return fail(ctx, DTA_ERR_INVALID_ARG, "need 0 <= rank < world <= 16");
+  if (!multicast_buffer || !sync_words) return fail(ctx, DTA_ERR_INVALID_ARG, "the in-backward exchange needs a multicast mapping and sync_words");
+  for (int r = 0; r < world; ++r) {
+    if (!peer_buffers[r]) return fail(ctx, DTA_ERR_INVALID_ARG, "peer_buffers[r] is NULL");
+    ctx->ex_peers[r] = peer_buffers[r];
+  }
+  ctx->ex_rank = rank; ctx->ex_world = world; ctx->ex_mc = multicast_buffer; ctx->ex_n4 = n_float4; ctx->ex_nd = n_double; ctx->ex_sync = sync_words;
   return DTA_OK;
 }
 
@@ -852,6 +880,25 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   const Splits sp = wgrad_splits(B);
   const size_t nsc = (size_t)B * classes;
   cudaError_t e;
+  // In-backward gradient exchange (dta_set_grad_exchange): only when the gradient table IS the registered symmetric buffer
+  // (first float32 gradient at its base, conv1 weight gradients inside it) -- otherwise the caller reduces afterwards.
+  ctx->exchanged = 0;
+  bool exchange = false;
+  unsigned long long ex_lo[2] = {0, 0}, ex_hi[2] = {0, 0};
+  int ex_nw = 0;
+  if (ctx->ex_world > 1 && tc_enabled_for_exchange(ctx) && grads->branch[0].conv[0].conv_w == ctx->ex_peers[ctx->ex_rank]) {
+    exchange = true;
+    const char* base = static_cast<const char*>(ctx->ex_peers[ctx->ex_rank]);
+    for (int g = 0; g < nb && exchange; ++g) {
+      const char* w = reinterpret_cast<const char*>(grads->branch[g].conv[0].conv_w);
+      const size_t bytes = (size_t)32 * bands * 9 * sizeof(float);
+      if (!w || w < base || w + bytes > base + ctx->ex_n4 * 16) { exchange = false; break; }
+      ex_lo[ex_nw] = (unsigned long long)(w - base) / 16;                 // rounded outward to whole float4
+      ex_hi[ex_nw] = (unsigned long long)((w - base) + bytes + 15) / 16;
+      if (ex_nw > 0 && ex_lo[ex_nw] < ex_hi[ex_nw - 1]) ex_lo[ex_nw] = ex_hi[ex_nw - 1];
+      ++ex_nw;
+    }
+  }
 
   // Side stream: everything off the critical path dgrad -> attention backward -> BatchNorm backward -> pack runs there:
   // parameter packing and gradient zero-fill first, then each block's weight gradient (+ split-K reduce) under the NEXT
@@ -1109,6 +1156,28 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
       DTA_CHECK_LAUNCH(ctx, "batched_reduce_finish");
     }
     if ((rc = bn_bwd(0)) != DTA_OK) return rc;
+    // Gradient exchange, part A (dta_set_grad_exchange): every gradient except conv1's weights is final once the kernels
+    // enqueued so far have run -- reduce them over the ranks now, on the auxiliary stream, under conv1's weight gradient.
+    if (exchange) {
+      ArRanges ra{};
+      unsigned long long pos = 0;
+      for (int k = 0; k < ex_nw; ++k) {                       // complement of conv1's weight ranges
+        if (ex_lo[k] > pos) { ra.lo[ra.n] = pos; ra.hi[ra.n] = ex_lo[k]; ++ra.n; }
+        pos = ex_hi[k];
+      }
+      if (pos < ctx->ex_n4) { ra.lo[ra.n] = pos; ra.hi[ra.n] = ctx->ex_n4; ++ra.n; }
+      ra.with_doubles = 1;
+      cudaStream_t xs = aux.on ? aux.stream() : (side.on ? ss : st);
+      if (aux.on) {
+        aux.wait_main();
+        if (side.on) { cudaEvent_t e2 = side.next_event(); cudaEventRecord(e2, ss); cudaStreamWaitEvent(xs, e2, 0); }
+      } else if (side.on) {
+        side.wait_main();
+      }
+      StageScope sc(ctx, "dist.grad_allreduce", xs);
+      if (ra.n > 0 && (rc = launch_allreduce(ctx, xs, ctx->ex_rank, ctx->ex_world, ctx->ex_peers, ctx->ex_mc, ctx->ex_n4, ctx->ex_nd, nullptr, ctx->ex_sync, ra, 0)) != DTA_OK)
+        return rc;
+    }
     ConvSrc dz = src_dz(W.da[0], L.z[0], nb * 32, nb * 32, 121, W.k0[0], W.k1[0], W.k2[0]);
     ConvSrc in = src_raw(x, bands, kHW);
     int conv1_nsplit = sp.n[0];
@@ -1127,6 +1196,14 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("conv1 wgrad: ") + cudaGetErrorString(e));
     ctx->launches++;
     if ((rc = reduce_w(0, bands, conv1_nsplit)) != DTA_OK) return rc;
+    if (exchange) {   // part B: conv1's weight gradient, right behind the kernel that produced it
+      ArRanges rb{};
+      for (int k = 0; k < ex_nw; ++k) { rb.lo[k] = ex_lo[k]; rb.hi[k] = ex_hi[k]; }
+      rb.n = ex_nw;
+      StageScope sc(ctx, "dist.grad_allreduce", ss);
+      if ((rc = launch_allreduce(ctx, ss, ctx->ex_rank, ctx->ex_world, ctx->ex_peers, ctx->ex_mc, ctx->ex_n4, ctx->ex_nd, nullptr, ctx->ex_sync, rb, 1)) != DTA_OK) return rc;
+      ctx->exchanged = 1;
+    }
     if (dx) return fail(ctx, DTA_ERR_UNSUPPORTED, "gradient of the crops (dx) is not built yet; the reference feeds requires_grad=False inputs");
   }
   side.join();

@@ -37,6 +37,13 @@ struct dta_ctx {
   cudaStream_t aux = nullptr;   // second side stream (option "overlap" = 2): work that must not queue behind the weight gradients
   std::vector<cudaEvent_t> sync_events;
   size_t sync_next = 0;
+  // gradient exchange performed by dta_backward itself (dta_set_grad_exchange); world <= 1: none registered
+  int ex_rank = 0, ex_world = 0;
+  void* ex_peers[16] = {};
+  const void* ex_mc = nullptr;
+  size_t ex_n4 = 0, ex_nd = 0;
+  void* ex_sync = nullptr;
+  int exchanged = 0;   // the last dta_backward exchanged its gradients
 };
 
 

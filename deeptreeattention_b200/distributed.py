@@ -77,14 +77,27 @@ class GradSync:
                 return False
         return True
 
+    def _refresh_alpha(self, averaged):
+        """alpha's float64 gradient is reduced in the buffer the backward wrote it to; autograd's AccumulateGrad keeps its OWN
+        copy in ``p.grad`` whenever that buffer is referenced elsewhere (it always is: the spec / the symmetric buffer), so the
+        mean has to be copied over it."""
+        for p in self.module.parameters():
+            if p.dtype == torch.float64 and p.grad is not None and p.grad.data_ptr() != averaged.data_ptr():
+                p.grad.copy_(averaged)
+
     def sync(self):
         if self.world == 1:
             self.last_path = "single"
             return
         spec = self.module.fused_spec() if hasattr(self.module, "fused_spec") else None
         if self.peer is not None and spec is not None and spec.flat_grad is self.peer.flat and self._flat_views_intact(spec):
+            if self.peer.in_backward and self.peer.exchanged():
+                # dta_backward already exchanged (two launches overlapped with conv1's weight gradient, dta_set_grad_exchange)
+                self.last_path = "peer-multimem-in-backward"
+                return
             # ONE kernel over NVLink peer memory: sum over ranks (in the switch when NVLS is available), mean, in place
             self.peer.allreduce()
+            self._refresh_alpha(self.peer.alpha)
             self.last_path = "peer-multimem" if self.peer.multicast_ptr else "peer-p2p"
             return
         if self._flat_views_intact(spec):
@@ -98,6 +111,8 @@ class GradSync:
                 for t in tensors:
                     dist.all_reduce(t, group=self.group)
                     t.div_(self.world)
+            if galpha is not None:
+                self._refresh_alpha(galpha)
             self.last_path = "flat"
             return
         by_dtype = {}
@@ -150,7 +165,7 @@ class _PeerBuffers:
             self.buf.zero_()
             self.handle = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
             self.scratch = torch.empty(scratch_bytes.value, dtype=torch.uint8, device=dev)
-            self.sync_words = torch.zeros(4, dtype=torch.int32, device=dev)
+            self.sync_words = torch.zeros(8, dtype=torch.int32, device=dev)
         self.peer_ptrs = (C.c_void_p * 16)(*[int(p) for p in self.handle.buffer_ptrs] + [None] * (16 - self.world))
         try:
             self.multicast_ptr = int(self.handle.multicast_ptr) if self.handle.has_multicast_support(dev.type, dev.index) else 0
@@ -160,8 +175,22 @@ class _PeerBuffers:
         self.alpha = self.buf[self.n4 * 16:self.n4 * 16 + 8].view(torch.float64).reshape(()) if ndouble else torch.zeros((), dtype=torch.float64, device=dev)
         self.device, self._capi, self._C = dev, _capi, C
         module.__dict__["_grad_buffers"] = (self.flat, self.alpha)
+        # Optional (DTA_EXCHANGE_IN_BACKWARD=1): the backward pass exchanges its gradients itself in two launches, everything but
+        # conv1's weights under conv1's weight-gradient kernel.  Measured SLOWER than the single exchange kernel after the
+        # backward pass (N = 2: 1.057 vs 1.033 ms per step, N = 8: 1.089 vs 1.035 ms; profiles/r05f_*): the spinning exchange CTAs
+        # take issue slots from the tensor kernel they hide under.  Off by default.
+        self.in_backward = False
+        if self.multicast_ptr and os.environ.get("DTA_EXCHANGE_IN_BACKWARD", "0") == "1":
+            handle = _capi.context(dev.index)
+            rc = lib.dta_set_grad_exchange(handle, self.rank, self.world, C.byref(self.peer_ptrs), self.multicast_ptr, self.n4, self.nd,
+                                           self.sync_words.data_ptr())
+            _capi.check(handle, rc, "dta_set_grad_exchange")
+            self.in_backward = True
         torch.cuda.synchronize(dev)
         dist.barrier(group)          # every rank's flag words are zero before anyone signals
+
+    def exchanged(self) -> bool:
+        return bool(self._capi.get_option(self.device.index, "exchanged"))
 
     def allreduce(self):
         dev = self.device

@@ -240,13 +240,23 @@ int dta_preprocess_crops(dta_ctx* ctx, const int16_t* raw, int batch, int bands_
  *                      at flags_offset (dta_grad_allreduce_sizes); the flag words must be zero before the first call.
  *   multicast_buffer : NVSwitch multicast mapping of the same buffers (multimem.ld_reduce sums in the switch), or NULL
  *                      (plain loads from every peer, summed in rank order)
- *   scratch          : scratch_bytes of local device memory; sync_words: 4 zero-initialised uint32 of local memory
+ *   scratch          : scratch_bytes of local device memory; sync_words: 8 zero-initialised uint32 of local memory
  * On return (stream order) the local buffer holds the MEAN over ranks; every rank must make the same call.
+ *
+ * dta_set_grad_exchange registers the same buffers with the context (multicast mapping required).  From then on a
+ * dta_backward whose gradient table starts at peer_buffers[rank] performs the exchange ITSELF, in two launches: everything
+ * but conv1's weight gradient as soon as it is final -- on a side stream, under conv1's weight-gradient kernel, the longest
+ * of the step -- and conv1's slice (0.85 of 2.9 MB) right behind that kernel.  dta_get_option("exchanged") tells whether the
+ * last backward did so (the caller then must not reduce again).  world <= 1 or peer_buffers == NULL unregisters.
+ * (Measured slower than the single dta_grad_allreduce launch after the backward pass on 2 and 8 B200s -- the spinning
+ * exchange CTAs compete with the tensor kernel they hide under -- so the Python side only registers it on request.)
  */
 int dta_grad_allreduce_sizes(size_t n_float4, size_t n_double, int world, size_t* buffer_bytes, size_t* flags_offset,
                              size_t* scratch_bytes);
 int dta_grad_allreduce(dta_ctx* ctx, int rank, int world, void* const peer_buffers[], const void* multicast_buffer,
                        size_t n_float4, size_t n_double, void* scratch, void* sync_words, void* cuda_stream);
+int dta_set_grad_exchange(dta_ctx* ctx, int rank, int world, void* const peer_buffers[], const void* multicast_buffer,
+                          size_t n_float4, size_t n_double, void* sync_words);
 
 /*
  * Year ensemble on the device.  learned_ensemble.forward (src/models/year.py:24-33) skips a year whose crop tensor sums to

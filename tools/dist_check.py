@@ -47,10 +47,17 @@ def main():
         gn = step(mn, sn, regime)
         torch.cuda.synchronize()
         worst = 0.0
+        bad = []
         for k in gn:
             assert k in gp, k
             scale = float(gn[k].abs().max()) + 1e-12
-            worst = max(worst, float((gp[k].double() - gn[k].double()).abs().max()) / scale)
+            d = float((gp[k].double() - gn[k].double()).abs().max()) / scale
+            worst = max(worst, d)
+            if d > 1e-5:
+                bad.append((round(d, 4), k))
+        if bad:
+            print(f"  rank {rank} tensors that differ:", sorted(bad, reverse=True)[:8], "alpha peer/nccl/buffer slot:",
+                  float(gp["alpha"]), float(gn["alpha"]), float(sp.peer.alpha), flush=True)
         # every rank must hold the same averaged gradient bits on the peer path
         flat = mp.fused_spec().flat_grad
         ref = flat.clone()
