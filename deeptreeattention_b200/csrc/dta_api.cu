@@ -62,8 +62,8 @@ struct Carver {
 // Tensor-core path geometry.  Two position streams: side 11 (conv1, conv2 and their gradients) and
 // side 5 (conv3).  Buffers are padded so that every kernel's tile size divides the stream length.
 using WgradCfg1 = TcWgrad<128, 128, true, 3, 2>;  // conv1: merged 64 output channels (hi/lo stacked), 128-channel slices, 3 tap groups
-using WgradCfg2 = TcWgrad<32, 128, true, 1, 2>;    // conv2: 64 output channels per branch, 32 input channels
-using WgradCfg3 = TcWgrad<32, 64, false, 1, 2>;    // conv3: 128 output channels per branch, 2 slices of 32 input channels
+using WgradCfg2 = TcWgrad<32, 128, true, 2, 2, true>;    // conv2: 64 output channels per branch, 32 input channels; hi|lo halves as one N = 64 operand, 2 tap groups
+using WgradCfg3 = TcWgrad<32, 64, false, 2, 2, true>;    // conv3: 128 output channels per branch, 2 slices of 32 input channels; N = 64, 2 tap groups
 constexpr int kTcSmCount = 148;              // split-K factors are sized for the B200's 148 SMs (dta_query_sizes has no device)
 
 struct TcSplit { int nkstage, nslices, nsplit, per; };
@@ -91,8 +91,8 @@ TcGeom tc_geom(int B, int bands, int nb) {
   g.nstage1 = (bands + 15) / 16;
   g.nchunk1 = (2 * g.nstage1 + WgradCfg1::BCH - 1) / WgradCfg1::BCH * WgradCfg1::BCH;   // whole weight-gradient slices
   g.w1 = tc_split(g.rows11, WgradCfg1::KROWS, g.nchunk1 * 8, WgradCfg1::NCI, 1, WgradCfg1::NTG);
-  g.w2 = tc_split(g.rows11, WgradCfg2::KROWS, 32, WgradCfg2::NCI, nb);
-  g.w3 = tc_split(g.rows5, WgradCfg3::KROWS, 64, WgradCfg3::NCI, nb);
+  g.w2 = tc_split(g.rows11, WgradCfg2::KROWS, 32, WgradCfg2::NCI, nb, WgradCfg2::NTG);
+  g.w3 = tc_split(g.rows5, WgradCfg3::KROWS, 64, WgradCfg3::NCI, nb, WgradCfg3::NTG);
   return g;
 }
 inline __nv_bfloat16* take_bf16(Carver& c, size_t n16) { return reinterpret_cast<__nv_bfloat16*>(c.take(n16 * 4)); }

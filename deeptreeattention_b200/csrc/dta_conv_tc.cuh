@@ -531,9 +531,14 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
 //   NTG tap groups: the 9 taps are split over NTG CTAs (blockIdx.x = slice*NTG + group) that stream the same operands
 //   (the second reader hits L2); fewer taps per CTA leave tensor-memory room for wider N, and the per-MMA cost is
 //   32 + N/4 cycles of shared-memory operand reads against an N/2 issue floor (tools/tc_rate.cu), so wider N is faster.
-template <int NCI_, int KROWS_, bool STACK_, int NTG_ = 1, int NSTAGE_ = 3>
+//   WIDE: the staged input slice is [in_hi chunks | in_lo chunks] with ONE chunk stride, so an MMA of N = 2 * NCI reads both
+//   halves as a single operand: columns [0, NCI) collect dz * in_hi, [NCI, 2 NCI) dz * in_lo, added in the epilogue.  For the
+//   32-channel slices of conv2 / conv3 that is one 48-cycle MMA instead of two 40-cycle ones per tap and K step.
+template <int NCI_, int KROWS_, bool STACK_, int NTG_ = 1, int NSTAGE_ = 3, bool WIDE_ = false>
 struct TcWgrad {
   static constexpr int NCI = NCI_;                         // input channels per CTA slice
+  static constexpr bool WIDE = WIDE_;
+  static constexpr int NW = WIDE ? 2 * NCI : NCI;          // fp32 columns of tensor memory per tap
   static constexpr int KROWS = KROWS_;                     // stream positions per stage
   static constexpr bool STACK = STACK_;
   static constexpr int NTG = NTG_;
@@ -549,7 +554,7 @@ struct TcWgrad {
   static constexpr int RED_BYTES = STACK ? 64 * NCI * 4 : 0;   // lo-half partials for the epilogue; aliases stage 0 (idle by then)
   static constexpr size_t SMEM_BYTES = (size_t)NSTAGE * STAGE_BYTES + 1024;
   static_assert(RED_BYTES <= STAGE_BYTES, "epilogue scratch must fit one stage");
-  static_assert(MAXT * NCI <= 512 && NCI % 16 == 0, "taps x NCI fp32 columns must fit tensor memory");
+  static_assert(MAXT * NW <= 512 && NCI % 16 == 0 && NW <= 256, "taps x columns per tap must fit tensor memory");
   static_assert(SMEM_BYTES <= 227 * 1024, "stage too large");
 };
 
@@ -617,6 +622,7 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows
   } else if (warp == 1) {
     const uint32_t leader = elect_one_sync();
     constexpr uint32_t idesc = tc::make_idesc_bf16(128, Cfg::NCI, 1, 1);
+    constexpr uint32_t idesc_wide = tc::make_idesc_bf16(128, Cfg::NW, 1, 1);
     for (int i = 0; i < nks; ++i) {
       const int st = i % Cfg::NSTAGE;
       const uint32_t ph = (i / Cfg::NSTAGE) & 1;
@@ -636,9 +642,13 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows
           const int t = tap0 + tl;
           const int arow = kTcGuard + kk * 16 - ((t / 3 - 1) * St::PT + (t % 3 - 1));   // dz row for input row kk*16
           if (leader && tl < ntap) {
-            const uint32_t dcol = tmem + tl * Cfg::NCI;
-            tc::mma_bf16(dcol, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + kk * 16, b_hi32), idesc, (i | kk) ? 1u : 0u);
-            tc::mma_bf16(dcol, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + B_LO_PLANE + kk * 16, b_hi32), idesc, 1u);
+            const uint32_t dcol = tmem + tl * Cfg::NW;
+            if (Cfg::WIDE) {
+              tc::mma_bf16(dcol, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + kk * 16, b_hi32), idesc_wide, (i | kk) ? 1u : 0u);
+            } else {
+              tc::mma_bf16(dcol, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + kk * 16, b_hi32), idesc, (i | kk) ? 1u : 0u);
+              tc::mma_bf16(dcol, desc_from(a_lo32 + arow, a_hi32), desc_from(b_lo32 + B_LO_PLANE + kk * 16, b_hi32), idesc, 1u);
+            }
             if (!Cfg::STACK)
               tc::mma_bf16(dcol, desc_from(a_lo32 + A_LO_PLANE + arow, a_hi32), desc_from(b_lo32 + kk * 16, b_hi32), idesc, 1u);
           }
@@ -662,7 +672,15 @@ tc_conv_wgrad_kernel(const __nv_bfloat16* __restrict__ dzp /*[2][dz_chunks][rows
       float v[Cfg::NCI];
       if (nks > 0) {
 #pragma unroll
-        for (int c0 = 0; c0 < Cfg::NCI; c0 += 16) tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + tl * Cfg::NCI + c0, v + c0);
+        for (int c0 = 0; c0 < Cfg::NCI; c0 += 16) tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + tl * Cfg::NW + c0, v + c0);
+        if (Cfg::WIDE) {      // add the dz * in_lo columns
+          float w[Cfg::NCI];
+#pragma unroll
+          for (int c0 = 0; c0 < Cfg::NCI; c0 += 16) tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + tl * Cfg::NW + Cfg::NCI + c0, w + c0);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < Cfg::NCI; ++j) v[j] += w[j];
+        }
         tc::tmem_ld_wait();
       } else {
 #pragma unroll

@@ -75,7 +75,13 @@ def test_fused_adam_trains_the_fused_model_and_reloads_state():
             o.zero_grad(set_to_none=True)
             loss = torch.nn.functional.cross_entropy(m(xd), yd)
             loss.backward()
-            o.step()
+        # both optimizers must see the SAME gradients: after the first step the two models differ by an ulp, which can flip
+        # a ReLU and move single gradient elements by far more than the optimizers' own rounding (Adam then amplifies it)
+        for p, q in zip(m1.parameters(), m2.parameters()):
+            if q.grad is not None:
+                p.grad.copy_(q.grad)
+        o1.step()
+        o2.step()
         losses.append(float(loss))
     for (k, p), q in zip(m1.named_parameters(), m2.parameters()):
         assert float((p.detach().double() - q.detach().double()).abs().max()) <= 1e-5 + 1e-5 * float(q.detach().abs().max()), k
