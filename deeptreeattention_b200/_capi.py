@@ -77,7 +77,7 @@ EXPORTS = ["dta_abi_version", "dta_create", "dta_destroy", "dta_last_error", "dt
            "dta_plane_mean", "dta_plane_mean_backward", "dta_conv_module_workspace_bytes", "dta_conv_module_forward",
            "dta_conv_module_backward", "dta_attention_sizes", "dta_attention_forward", "dta_attention_backward",
            "dta_classifier_forward", "dta_classifier_backward", "dta_adam_step", "dta_forward_pair", "dta_crops_nonzero",
-           "dta_ensemble_mean", "dta_metadata_sizes", "dta_metadata_forward", "dta_metadata_backward", "dta_set_grad_exchange"]
+           "dta_ensemble_mean", "dta_metadata_sizes", "dta_metadata_forward", "dta_metadata_backward", "dta_set_grad_exchange", "dta_set_update_gate"]
 
 
 def sources():
@@ -191,6 +191,7 @@ def lib():
         L.dta_forward_pair.argtypes = [vp, C.POINTER(Shape), ci, vp, C.POINTER(Tensors), C.POINTER(C.c_void_p * 6), vp, vp, vp]
         L.dta_crops_nonzero.argtypes = [vp, ci, C.POINTER(C.c_void_p * 16), sz, vp, vp, vp]
         L.dta_ensemble_mean.argtypes = [vp, ci, C.POINTER(C.c_void_p * 16), vp, ci, ci, ci, vp, vp]
+        L.dta_set_update_gate.argtypes = [vp, vp]
         L.dta_set_grad_exchange.argtypes = [vp, ci, ci, C.POINTER(C.c_void_p * 16), vp, sz, sz, vp]
         L.dta_metadata_sizes.argtypes = [ci, ci, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.dta_metadata_forward.argtypes = [vp, ci, ci, ci, ci, vp, vp, C.POINTER(MetadataTensors), vp, C.c_uint64, vp, vp, vp]
@@ -253,6 +254,12 @@ def saved_region(net_kind: int, batch: int, bands: int, classes: int, training: 
 # Diagnostics (parity tests): when True, every fused forward leaves a reference to its ``saved`` buffer in the module's
 # spec (``model.fused_spec().last_saved``) so that the convolution outputs can be read back with ``saved_region``.
 KEEP_SAVED = False
+
+
+def set_update_gate(device_index: int, flag_ptr):
+    """Registers (or, with None / 0, clears) the device flag that gates BatchNorm running-statistics updates (dta_set_update_gate)."""
+    ctx = context(device_index)
+    check(ctx, lib().dta_set_update_gate(ctx, flag_ptr or None), "dta_set_update_gate")
 
 
 def set_option(device_index: int, key: str, value: int):

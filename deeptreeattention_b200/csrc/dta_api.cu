@@ -489,6 +489,12 @@ int dta_set_option(dta_ctx* ctx, const char* key, int64_t value) {
   return fail(ctx, DTA_ERR_INVALID_ARG, std::string("unknown option ") + key);
 }
 
+int dta_set_update_gate(dta_ctx* ctx, const float* gate) {
+  if (!ctx) return DTA_ERR_INVALID_ARG;
+  ctx->update_gate = gate;
+  return DTA_OK;
+}
+
 int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value) {
   if (!ctx || !key || !value) return DTA_ERR_INVALID_ARG;
   if (!strcmp(key, "conv_impl")) { *value = ctx->conv_impl; return DTA_OK; }
@@ -635,7 +641,7 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
     StageScope sc(ctx, "fwd.bn_finalize", st);
     const int ctot = nb * kC[k];
     launch_k(bn_fwd_finalize_kernel, (ctot + kBnCh - 1) / kBnCh, kBnCh * kBnSlices, 0, st, W.stats, nblk_k, ctot, (double)B * kHWpre[k], bn_params(params, d, k),
-                                                                    shape->training, L.bn_mean[k], L.bn_istd[k], L.bn_scale[k], L.bn_shift[k]);
+                                                                    shape->training, L.bn_mean[k], L.bn_istd[k], L.bn_scale[k], L.bn_shift[k], ctx->update_gate);
     DTA_CHECK_LAUNCH(ctx, "bn_fwd_finalize");
     return DTA_OK;
   };

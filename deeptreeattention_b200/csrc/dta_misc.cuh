@@ -92,7 +92,7 @@ __device__ __forceinline__ void bn_block_sum2(double& a, double& b, double (*sa)
 __global__ void __launch_bounds__(kBnCh * kBnSlices)
 bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int nblk, int ctot, double count, BnParams bn,
                        int training, float* __restrict__ mean, float* __restrict__ istd, float* __restrict__ scale,
-                       float* __restrict__ shift) {
+                       float* __restrict__ shift, const float* __restrict__ update_gate /*null, or: running statistics only move if *gate != 0*/) {
   pdl_prologue();
   __shared__ double ss[kBnSlices * kBnCh / 32][kBnCh], sq[kBnSlices * kBnCh / 32][kBnCh];
   const int cx = threadIdx.x & (kBnCh - 1), ry = threadIdx.x / kBnCh;
@@ -121,9 +121,11 @@ bn_fwd_finalize_kernel(const float* __restrict__ part /*[nblk][ctot][2]*/, int n
     m = (float)mu;
     is = (float)(1.0 / sqrt(var + (double)kBnEps));
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    bn.rm[br][c] = (float)((1.0 - kBnMomentum) * (double)p_rm + kBnMomentum * mu);
-    bn.rv[br][c] = (float)((1.0 - kBnMomentum) * (double)p_rv + kBnMomentum * unbiased);
-    if (c == 0 && bn.nbt[br] != nullptr) bn.nbt[br][0] += 1;
+    if (update_gate == nullptr || __ldg(update_gate) != 0.f) {
+      bn.rm[br][c] = (float)((1.0 - kBnMomentum) * (double)p_rm + kBnMomentum * mu);
+      bn.rv[br][c] = (float)((1.0 - kBnMomentum) * (double)p_rv + kBnMomentum * unbiased);
+      if (c == 0 && bn.nbt[br] != nullptr) bn.nbt[br][0] += 1;
+    }
   } else {
     m = p_rm;
     is = (float)(1.0 / sqrt((double)p_rv + (double)kBnEps));

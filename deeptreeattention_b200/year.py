@@ -1,11 +1,16 @@
 """Drop-in for the reference's ``src/models/year.py``: one spectral network per year, all-zero years skipped,
 mean of the last-head scores (reference :9-33).  Every year network runs through the CUDA library.
 
-Training keeps the reference's control flow (a skipped year must not touch its BatchNorm statistics, so the zero test
-has to reach the host -- ONE sync for all years instead of the reference's one per year).  Inference
-(``eval()`` under ``torch.no_grad()``: validation / predict) never leaves the device: ``dta_crops_nonzero`` computes the
-per-year flags, every year network runs, and ``dta_ensemble_mean`` averages the flagged years (optionally fused with the
-softmax of ``MultiStage.predict_step``), so the whole ensemble is stream-ordered and graph-capturable."""
+Neither mode leaves the device.  ``dta_crops_nonzero`` computes the per-year "not all zero" flags (the reference's
+``if x.sum() == 0: continue``, a device->host sync per year, year.py:27).
+Inference (``eval()`` under ``torch.no_grad()``: validation / predict): every year network runs and ``dta_ensemble_mean``
+averages the flagged years (optionally fused with the softmax of ``MultiStage.predict_step``).
+Training: every year network runs with its flag registered as the library's update gate (``dta_set_update_gate``: the
+BatchNorm running statistics of a flagged-out year stay untouched, as if it had not run), and the flagged years' last-head
+scores are averaged with the flags as weights, so a skipped year receives exactly zero gradient (the reference leaves its
+``.grad`` at ``None``).  The whole ensemble is stream-ordered and CUDA-graph capturable; the price is the arithmetic of the
+skipped years.  ``host_skip=True`` restores the reference's control flow (one host sync for all years, skipped years not
+computed)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -77,10 +82,11 @@ class learned_ensemble(Module):
     """``learned_ensemble(years, classes, config)`` with ``config["bands"]`` and ``config["pretrain_state_dict"]``
     exactly as in the reference (year.py:10-22)."""
 
-    def __init__(self, years, classes, config):
+    def __init__(self, years, classes, config, host_skip: bool = False):
         super().__init__()
         self.year_models = nn.ModuleList()
         self.years = years
+        self.host_skip = host_skip
         for _ in range(years):
             if config.get("pretrain_state_dict"):
                 base_model = Hang2020.load_from_backbone(state_dict=config["pretrain_state_dict"], classes=classes, bands=config["bands"])
@@ -96,11 +102,26 @@ class learned_ensemble(Module):
             flags = crops_nonzero(images)
             year_scores = [self.year_models[index](x)[-1] for index, x in enumerate(images)]
             return ensemble_mean(year_scores, flags)
-        # training / autograd: a skipped year must not run at all -- one host sync for all years instead of one per year
-        sums = torch.stack([x.sum() for x in images]).tolist()
-        year_scores: List[torch.Tensor] = []
-        for index, x in enumerate(images):
-            if sums[index] == 0:
-                continue
-            year_scores.append(self.year_models[index](x)[-1])
-        return torch.stack(year_scores, axis=1).mean(axis=1)
+        if self.host_skip:
+            # the reference's control flow: a skipped year does not run at all -- one host sync for all years
+            sums = torch.stack([x.sum() for x in images]).tolist()
+            year_scores: List[torch.Tensor] = []
+            for index, x in enumerate(images):
+                if sums[index] == 0:
+                    continue
+                year_scores.append(self.year_models[index](x)[-1])
+            return torch.stack(year_scores, axis=1).mean(axis=1)
+        # training / autograd on the device: flags gate the BatchNorm buffer updates and weight the mean
+        flags = crops_nonzero(images)
+        dev = images[0].device
+        index = dev.index if dev.index is not None else torch.cuda.current_device()
+        year_scores = []
+        try:
+            for y, x in enumerate(images):
+                _capi.set_update_gate(index, flags[y:y + 1].data_ptr() if self.training else None)
+                year_scores.append(self.year_models[y](x)[-1])
+        finally:
+            _capi.set_update_gate(index, None)
+        stacked = torch.stack(year_scores, dim=1)                        # (B, years, classes)
+        weights = (flags / flags.sum()).view(1, -1, 1)                   # no active year: NaN rows (the reference raises)
+        return (stacked * weights).sum(dim=1)

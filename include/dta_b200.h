@@ -267,6 +267,13 @@ int dta_set_grad_exchange(dta_ctx* ctx, int rank, int world, void* const peer_bu
  *                       F.softmax(dim=1) when softmax != 0 (MultiStage.validation_step / predict_step,
  *                       multi_stage.py:302,314).  No active year gives NaN rows (the reference raises on the empty stack).
  */
+/* Device-side skip for the year ensemble in TRAINING: the reference does not run a year network whose crops are all zero
+ * (year.py:27), so its BatchNorm buffers stay untouched.  With a gate registered (one float in device memory, e.g. one
+ * element of dta_crops_nonzero's flags), training-mode dta_forward calls still compute the network but update
+ * running_mean / running_var / num_batches_tracked only if *gate != 0 when the kernel runs -- the caller masks the year out
+ * of the ensemble mean (and with it every gradient) with the same flag, and no value ever travels to the host.
+ * gate == NULL (default) restores the unconditional update. */
+int dta_set_update_gate(dta_ctx* ctx, const float* gate);
 int dta_crops_nonzero(dta_ctx* ctx, int n_years, const float* const crops[], size_t elems, float* flags, void* workspace,
                       void* cuda_stream);
 int dta_ensemble_mean(dta_ctx* ctx, int n_years, const float* const scores[], const float* flags, int batch, int classes,

@@ -81,13 +81,60 @@ def test_crops_nonzero_and_ensemble_mean():
 
 
 @pytest.mark.gpu
-def test_training_ensemble_leaves_skipped_year_untouched():
-    """train(): the zero year is skipped on the host like the reference, so its BatchNorm statistics do not move."""
+@pytest.mark.parametrize("host_skip", [False, True])
+def test_training_ensemble_leaves_skipped_year_untouched(host_skip):
+    """train(): the all-zero year (year.py:27) must not move its BatchNorm buffers, must not contribute to the mean and gets no
+    gradient -- on the device (flag-gated buffer update, flag-weighted mean; no host sync) as with the reference's control
+    flow (host_skip=True); both agree with each other and with the oracle's mean over the live years."""
     from deeptreeattention_b200 import year
     torch.manual_seed(1)
-    m = year.learned_ensemble(years=2, classes=4, config={"bands": 20, "pretrain_state_dict": None}).cuda().train()
-    images = [torch.zeros(5, 20, 11, 11).cuda(), orc.make_inputs(5, 20, 4, 5)[0].cuda()]
-    out = m(images)
-    out.sum().backward()
-    assert int(m.year_models[0].conv1.bn1.num_batches_tracked) == 0 and int(m.year_models[1].conv1.bn1.num_batches_tracked) == 1
-    assert m.year_models[0].conv1.conv_layer.weight.grad is None and m.year_models[1].conv1.conv_layer.weight.grad is not None
+    m = year.learned_ensemble(years=3, classes=4, config={"bands": 20, "pretrain_state_dict": None}, host_skip=host_skip).cuda().train()
+    before = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    xs = [orc.make_inputs(5, 20, 4, 4)[0], torch.zeros(5, 20, 11, 11), orc.make_inputs(5, 20, 4, 5)[0]]
+    y = orc.make_inputs(5, 20, 4, 5)[1]
+    out = m([x.cuda() for x in xs])
+    torch.nn.functional.cross_entropy(out, y.cuda()).backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    # buffers: years 0 and 2 stepped once, year 1 bit-identical to before
+    for k, v in m.state_dict().items():
+        if orc.is_buffer(k):
+            if k.startswith("year_models.1."):
+                assert torch.equal(v, before[k]), k
+            elif k.endswith("num_batches_tracked"):
+                assert int(v) == 1, k
+    # the mean over the live years, against the oracle in train mode on the same parameters
+    ref = []
+    for i in (0, 2):
+        table = {k[len(f"year_models.{i}."):]: v.cpu() for k, v in before.items() if k.startswith(f"year_models.{i}.")}
+        ref.append(orc.forward("spectral", table, xs[i], training=True)[0][-1])
+    np.testing.assert_allclose(out.detach().cpu().numpy(), torch.stack(ref, 1).mean(1).detach().numpy(), rtol=0, atol=1e-3)
+    g1 = m.year_models[1].conv1.conv_layer.weight.grad
+    assert g1 is None or float(g1.abs().max()) == 0.0           # reference: None (the year never ran)
+    for i in (0, 2):
+        g = m.year_models[i].conv1.conv_layer.weight.grad
+        assert g is not None and float(g.abs().max()) > 0.0
+
+
+@pytest.mark.gpu
+def test_training_ensemble_device_skip_equals_host_skip():
+    """Same seed, same crops: the device-gated path and the reference's host-side skip give the same scores and gradients."""
+    from deeptreeattention_b200 import year
+    xs = [orc.make_inputs(6, 12, 3, 8)[0].cuda(), torch.zeros(6, 12, 11, 11).cuda(), orc.make_inputs(6, 12, 3, 9)[0].cuda()]
+    y = orc.make_inputs(6, 12, 3, 9)[1].cuda()
+    runs = []
+    for host_skip in (False, True):
+        torch.manual_seed(5)
+        m = year.learned_ensemble(years=3, classes=3, config={"bands": 12, "pretrain_state_dict": None}, host_skip=host_skip).cuda().train()
+        out = m(xs)
+        torch.nn.functional.cross_entropy(out, y).backward()
+        runs.append((out.detach(), {k: p.grad for k, p in m.named_parameters()}, {k: v.clone() for k, v in m.state_dict().items()}))
+    np.testing.assert_allclose(runs[0][0].cpu().numpy(), runs[1][0].cpu().numpy(), rtol=0, atol=1e-6)
+    for k, g in runs[1][1].items():
+        if g is None:
+            assert runs[0][1][k] is None or float(runs[0][1][k].abs().max()) == 0.0, k
+        else:
+            scale = float(g.abs().max())
+            assert float((runs[0][1][k] - g).abs().max()) <= 1e-5 * scale + 1e-8, k
+    for k, v in runs[1][2].items():
+        assert torch.allclose(runs[0][2][k].float(), v.float(), rtol=1e-6, atol=1e-7), k
