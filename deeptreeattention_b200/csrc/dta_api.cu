@@ -606,7 +606,8 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
     {
       StageScope sc(ctx, "fwd.conv1_pack", st);
       if (!ctx->fuse_x) DTA_TC_CHECK(run_tc_pack<11>(ctx, st, src_raw(x, bands, kHW), 1, B, tg.nchunk1, tg.rows11, L.xp), "tc_pack_stream(x)");
-      launch_k(tc_pack_w_fprop_kernel<64>, ctx->sm_count, 256, 0, st, conv_w(0), nb, 32, bands, tg.nstage1, 0, W.wpf[0]);
+      // on the critical path in front of conv1: one thread per weight element, the whole table in flight at once
+      launch_k(tc_pack_w_fprop_kernel<64>, (tg.nstage1 * 9 * 2 * 64 * 8 + 255) / 256, 256, 0, st, conv_w(0), nb, 32, bands, tg.nstage1, 0, W.wpf[0]);
       DTA_CHECK_LAUNCH(ctx, "tc_pack_w_fprop");
     }
     {

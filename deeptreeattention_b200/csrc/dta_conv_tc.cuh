@@ -164,17 +164,16 @@ template <int NCO>
 __global__ void tc_pack_w_fprop_kernel(Ptr2 w, int nb, int cout_b, int cin, int nstage, int mode, __nv_bfloat16* __restrict__ dst) {
   pdl_prologue();
   const int G = mode == 0 ? 1 : nb;
-  const size_t per_group = (size_t)nstage * 9 * 2 * (2 * NCO) * 8;
-  const size_t total = per_group * G;
+  // one thread = one weight element: a single (gathering) load yields both its hi and its lo row
+  const size_t total = (size_t)G * nstage * 9 * 2 * NCO * 8;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     size_t r = i;
     const int j = (int)(r % 8); r /= 8;
-    const int row = (int)(r % (2 * NCO)); r /= (2 * NCO);
+    const int n = (int)(r % NCO); r /= NCO;
     const int kc = (int)(r % 2); r /= 2;
     const int tap = (int)(r % 9); r /= 9;
     const int stage = (int)(r % nstage); r /= nstage;
     const int g = (int)r;
-    const int half = row / NCO, n = row - half * NCO;
     const int k = stage * 16 + kc * 8 + j;
     float v = 0.f;
     if (mode == 0) {
@@ -186,7 +185,9 @@ __global__ void tc_pack_w_fprop_kernel(Ptr2 w, int nb, int cout_b, int cin, int 
       if (n < cin && k < cout_b) v = __ldg(w.p[g] + ((size_t)k * cin + n) * 9 + (8 - tap));
     }
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    dst[i] = half == 0 ? h : __float2bfloat16_rn(v - __bfloat162float(h));
+    const size_t o = ((((((size_t)g * nstage + stage) * 9 + tap) * 2 + kc) * (2 * NCO)) + n) * 8 + j;
+    dst[o] = h;
+    dst[o + (size_t)NCO * 8] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
 
