@@ -37,6 +37,23 @@ _ATTN_FIELDS = {
 }
 
 
+# Every (re)registration of a parameter, buffer or sub-module anywhere in the process bumps this counter (torch's global
+# registration hooks fire from Module.__setattr__ / register_*): the fused networks cache their name / tensor lists and only
+# trust them while the counter stands still.  Swapping a head (net.classifier3 = Classifier(...)), a sub-network or a single
+# Parameter is therefore picked up like the reference nn.Module does, at the cost of one integer comparison per call.
+_STRUCTURE_VERSION = [0]
+
+
+def _bump_structure_version(*_args):
+    _STRUCTURE_VERSION[0] += 1
+    return None
+
+
+nn.modules.module.register_module_parameter_registration_hook(_bump_structure_version)
+nn.modules.module.register_module_buffer_registration_hook(_bump_structure_version)
+nn.modules.module.register_module_module_registration_hook(_bump_structure_version)
+
+
 def _fill_tensors(kind: int, ptr_of: Dict[str, int]) -> _capi.Tensors:
     """Build the C parameter (or gradient) table from {state_dict key: device pointer}."""
     t = _capi.Tensors()
@@ -216,10 +233,8 @@ class _FusedNet(Module):
         if x.dim() != 4 or x.shape[1] != self._bands or x.shape[2] != 11 or x.shape[3] != 11:
             raise ValueError(f"expected crops of shape (B, {self._bands}, 11, 11), got {tuple(x.shape)}")
         x = x.contiguous()
-        # the cached name/tensor lists are valid only while every parameter and buffer OBJECT is the one they were built
-        # from: swapping a head (net.classifier3 = Classifier(...)), a sub-network or a single tensor must be picked up like
-        # the reference nn.Module does
-        ident = tuple(map(id, self.parameters())) + tuple(map(id, self.buffers()))
+        # the cached name/tensor lists are valid only while no parameter, buffer or sub-module has been (re)registered
+        ident = _STRUCTURE_VERSION[0]
         cache = self.__dict__.get("_fused_cache")
         if cache is not None and cache[4] != ident:
             cache = None
