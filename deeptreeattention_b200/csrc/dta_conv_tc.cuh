@@ -416,9 +416,54 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int c = 0; c < NGRP; ++c) { run_sum[a][c] = 0.f; run_sq[a][c] = 0.f; }
+    // BatchNorm partial sums of this thread's positions, kept in registers ACROSS the CTA's tiles: the warp-level butterfly
+    // (62 shuffles per 32 channels, a quarter of the epilogue's instructions and most of its MIO pressure) runs once per
+    // group instead of once per tile.  A CTA walks its work items in order, so the group changes at most G - 1 times.
+    constexpr int GW = CH_PER < 32 ? CH_PER : 32;        // channels in a group
+    float ps[NGRP][GW], pq[NGRP][GW];
+#pragma unroll
+    for (int grp = 0; grp < NGRP; ++grp)
+#pragma unroll
+      for (int j = 0; j < GW; ++j) { ps[grp][j] = 0.f; pq[grp][j] = 0.f; }
+    auto flush_stats = [&](int gflush) {
+#pragma unroll
+      for (int grp = 0; grp < NGRP; ++grp) {
+        // halving butterfly: after log2(32) rounds lane l holds the warp total of channel cg0 + (l % GW)
+        float rs = 0.f, rq = 0.f;
+        if (GW == 32) {
+#pragma unroll
+          for (int w = 16; w >= 1; w >>= 1) {
+            const bool upper = (lane & w) != 0;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float keep_s = upper ? ps[grp][j + w] : ps[grp][j], send_s = upper ? ps[grp][j] : ps[grp][j + w];
+              const float keep_q = upper ? pq[grp][j + w] : pq[grp][j], send_q = upper ? pq[grp][j] : pq[grp][j + w];
+              ps[grp][j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+              pq[grp][j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+            }
+          }
+          rs = ps[grp][0]; rq = pq[grp][0];
+        } else {   // GW == 16: plain xor-reduce of 16 values, lane l reports channel l % 16
+#pragma unroll
+          for (int j = 0; j < GW; ++j) {
+            float a = ps[grp][j], c = pq[grp][j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+            if ((lane % GW) == j) { rs = a; rq = c; }
+          }
+        }
+        run_sum[gflush & 1][grp] += rs;
+        run_sq[gflush & 1][grp] += rq;
+#pragma unroll
+        for (int j = 0; j < GW; ++j) { ps[grp][j] = 0.f; pq[grp][j] = 0.f; }
+      }
+    };
+    int cur_g = -1;
     uint32_t tile_it = 0;
     for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++tile_it) {
       const int g = work / ntiles, tile = work - g * ntiles;
+      if (stats != nullptr && g != cur_g && cur_g >= 0) flush_stats(cur_g);
+      cur_g = g;
       const uint32_t acc = tile_it % Cfg::NACC, acc_use = tile_it / Cfg::NACC;
       float* sb = s_bias[tile_it & 1];
       if (et < NCO) {
@@ -432,10 +477,6 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
       tc::fence_after_sync();
 #pragma unroll
       for (int grp = 0; grp < NGRP; ++grp) {
-        constexpr int GW = CH_PER < 32 ? CH_PER : 32;        // channels in this group
-        float ps[GW], pq[GW];                                 // this thread's sums over its positions of the tile
-#pragma unroll
-        for (int j = 0; j < GW; ++j) { ps[j] = 0.f; pq[j] = 0.f; }
         const int cg0 = chalf * CH_PER + grp * 32;
 #pragma unroll 1
         for (int s = 0; s < Cfg::SUB; ++s) {
@@ -459,49 +500,21 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
                 for (int j = 0; j < 16; ++j) {
                   const float o = v0[j] + v1[j] + sb[c0 + j];
                   orow[(size_t)(c0 + j) * (S * S)] = o;
-                  ps[cc + j] += o;
-                  pq[cc + j] = fmaf(o, o, pq[cc + j]);
+                  ps[grp][cc + j] += o;
+                  pq[grp][cc + j] = fmaf(o, o, pq[grp][cc + j]);
                 }
               }
             }
           }
-        }
-        if (stats != nullptr) {
-          // halving butterfly: after log2(32) rounds lane l holds the warp total of channel cg0 + (l % GW)
-          float rs = 0.f, rq = 0.f;
-          if (GW == 32) {
-#pragma unroll
-            for (int w = 16; w >= 1; w >>= 1) {
-              const bool upper = (lane & w) != 0;
-#pragma unroll
-              for (int j = 0; j < w; ++j) {
-                const float keep_s = upper ? ps[j + w] : ps[j], send_s = upper ? ps[j] : ps[j + w];
-                const float keep_q = upper ? pq[j + w] : pq[j], send_q = upper ? pq[j] : pq[j + w];
-                ps[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
-                pq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
-              }
-            }
-            rs = ps[0]; rq = pq[0];
-          } else {   // GW == 16: plain xor-reduce of 16 values, lane l reports channel l % 16
-#pragma unroll
-            for (int j = 0; j < GW; ++j) {
-              float a = ps[j], c = pq[j];
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
-              if ((lane % GW) == j) { rs = a; rq = c; }
-            }
-          }
-          run_sum[g & 1][grp] += rs;
-          run_sq[g & 1][grp] += rq;
         }
       }
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
     }
+    if (stats != nullptr && cur_g >= 0) flush_stats(cur_g);
     if (stats != nullptr) {
       // partial statistics of this warp's positions: row (cta*4 + quad), channel (g*cout_g + chalf*CH_PER + 32*grp + lane)
-      constexpr int GW = CH_PER < 32 ? CH_PER : 32;
       float* srow = stats + ((size_t)blockIdx.x * 4 + quad) * out_ctot * 2;
       for (int g = 0; g < G && g < 2; ++g)
 #pragma unroll
