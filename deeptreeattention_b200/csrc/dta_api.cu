@@ -309,6 +309,7 @@ cudaError_t run_tc_pack(dta_ctx* ctx, cudaStream_t st, const ConvSrc& src, int G
   if (blocks > (size_t)ctx->sm_count * 16) blocks = (size_t)ctx->sm_count * 16;
   const int grid = (int)blocks;
   if (src.mode == SRC_RAW) launch_k(tc_pack_stream_kernel<S, SRC_RAW, false>, grid, 256, 0, st, src, G, B, nchunk, rows, dst);
+  else if (src.mode == SRC_DZ && src.pool) launch_k(tc_pack_stream_kernel<S, SRC_DZ, true>, grid, 256, 0, st, src, G, B, nchunk, rows, dst);
   else if (src.mode == SRC_DZ) launch_k(tc_pack_stream_kernel<S, SRC_DZ, false>, grid, 256, 0, st, src, G, B, nchunk, rows, dst);
   else if (src.pool) launch_k(tc_pack_stream_kernel<S, SRC_ACT, true>, grid, 256, 0, st, src, G, B, nchunk, rows, dst);
   else launch_k(tc_pack_stream_kernel<S, SRC_ACT, false>, grid, 256, 0, st, src, G, B, nchunk, rows, dst);
@@ -327,10 +328,16 @@ ConvSrc src_act(const float* z, int cin, int nb, int src_hw, int pool, const flo
   s.gate_mode[0] = btype[0]; s.gate_mode[1] = btype[1];
   return s;
 }
+// compact_cells > 0: `da` is the compact form the pooled attention backward writes -- B * ctot * compact_cells values followed
+// by as many arg-max bytes (compact_cells = pooled cells per channel plane)
 ConvSrc src_dz(const float* da, const float* z, int cin, int ctot, int hw, const float* k0, const float* k1,
-               const float* k2) {
+               const float* k2, int B = 0, int compact_cells = 0) {
   ConvSrc s{};
   s.mode = SRC_DZ; s.cin = cin; s.ctot = ctot; s.src_hw = hw; s.a = da; s.b = z; s.k0 = k0; s.k1 = k1; s.k2 = k2;
+  if (compact_cells > 0) {
+    s.pool = 1;
+    s.arg = reinterpret_cast<const unsigned char*>(da + (size_t)B * ctot * compact_cells);
+  }
   return s;
 }
 
@@ -1067,12 +1074,12 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn3", st);
     launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[2], L.bn_scale[2], L.bn_shift[2], L.bn_mean[2], L.bn_istd[2], attn_prm(2), classes, L.att[2], L.feat[2],
-                                              ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow[2]);
+                                              ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow[2], tcp ? 1 : 0);
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<3>");
     if ((rc = attn_param_grads(2)) != DTA_OK) return rc;
     if ((rc = bn_bwd(2)) != DTA_OK) return rc;
-    ConvSrc dz = src_dz(W.da[2], L.z[2], 128, nb * 128, 25, W.k0[2], W.k1[2], W.k2[2]);
+    ConvSrc dz = src_dz(W.da[2], L.z[2], 128, nb * 128, 25, W.k0[2], W.k1[2], W.k2[2], B, tcp ? 4 : 0);
     ConvSrc in = src_act(L.z[1], 64, nb, 121, 1, L.bn_scale[1], L.bn_shift[1], L.att[1], 3 * kAttRow[1], 2 * kAttRow[1], d.btype);
     side.join();   // packed input-gradient weights (and the gradient zero-fill) are done
     if (tcp) {
@@ -1106,12 +1113,12 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn2", st);
     launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[1], L.bn_scale[1], L.bn_shift[1], L.bn_mean[1], L.bn_istd[1], attn_prm(1), classes, L.att[1], L.feat[1],
-                                              ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow[1]);
+                                              ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow[1], tcp ? 1 : 0);
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<2>");
     if ((rc = attn_param_grads(1)) != DTA_OK) return rc;
     if ((rc = bn_bwd(1)) != DTA_OK) return rc;
-    ConvSrc dz = src_dz(W.da[1], L.z[1], 64, nb * 64, 121, W.k0[1], W.k1[1], W.k2[1]);
+    ConvSrc dz = src_dz(W.da[1], L.z[1], 64, nb * 64, 121, W.k0[1], W.k1[1], W.k2[1], B, tcp ? 25 : 0);
     ConvSrc in = src_act(L.z[0], 32, nb, 121, 0, L.bn_scale[0], L.bn_shift[0], L.att[0], 3 * kAttRow[0], 2 * kAttRow[0], d.btype);
     if (tcp) {
       { StageScope sc(ctx, "bwd.conv2_pack", st); DTA_TC_CHECK(run_tc_pack<11>(ctx, st, dz, nb, B, nb * 8, tg.rows11, W.dzp[1]), "tc_pack_stream(dz2)"); }
@@ -1144,7 +1151,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn1", st);
     launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[0], L.bn_scale[0], L.bn_shift[0], L.bn_mean[0], L.bn_istd[0], attn_prm(0), classes, L.att[0], L.feat[0],
-                                              ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow[0]);
+                                              ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow[0], 0);
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<1>");
     if ((rc = attn_param_grads(0)) != DTA_OK) return rc;

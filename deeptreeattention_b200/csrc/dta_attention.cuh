@@ -378,8 +378,8 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
                 const float* __restrict__ mean, const float* __restrict__ istd, AttnParams prm, int classes,
                 const float* __restrict__ att, const float* __restrict__ feat_unused,
                 Ptr2 dscores /*per branch [B][classes] or null*/, const float* __restrict__ dout /*[B][G][C][HW] or null*/,
-                float* __restrict__ da /*[B][G*C][HWPRE]*/, float* __restrict__ bnrow /*[B][G][2C]*/,
-                float* __restrict__ prow /*[B][G][ROW_LD]*/) {
+                float* __restrict__ da /*[B][G*C][HWPRE]; compact: [B][G*C][HW] values, then [B][G*C][HW] arg-max bytes*/,
+                float* __restrict__ bnrow /*[B][G][2C]*/, float* __restrict__ prow /*[B][G][ROW_LD]*/, int compact) {
   pdl_prologue();
   using Cfg = AttnCfg<C, SPRE, POOL>;
   using Row = AttnBwdRow<C, SPRE, POOL>;
@@ -597,7 +597,28 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
   // route through max-pool (argmax) and ReLU; emit da and the BatchNorm-backward partials
   float* da_out = da + ((size_t)b * G + g) * C * HWPRE;
   float* bn_row = bnrow + ((size_t)b * G + g) * 2 * C;
-  if (POOL) {
+  if (POOL && compact) {
+    // Pooled block, compact form: da is zero except at the arg-max of every 2x2 window, so only (value, slot) per pooled cell
+    // travel to the pack kernel (tc_pack_stream_kernel<S, SRC_DZ, true>): a quarter of the bytes, contiguous stores.
+    float* dvc = da + ((size_t)b * G + g) * C * HW;
+    unsigned char* darg = reinterpret_cast<unsigned char*>(da + (size_t)gridDim.x * G * C * HW) + ((size_t)b * G + g) * C * HW;
+    for (int i = tid; i < C * HW; i += kAttnThreads) {
+      const int c = i / HW;
+      const float dv = s_r[i] > 0.f ? s_D[i] : 0.f;
+      dvc[i] = dv;
+      darg[i] = s_arg[i];
+      s_D[i] = dv;
+      s_r[i] = dv * ((s_zarg[i] - s_part[c]) * s_part[C + c]);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += kAttnThreads) {
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll 5
+      for (int cell = 0; cell < HW; ++cell) { s1 += s_D[c * HW + cell]; s2 += s_r[c * HW + cell]; }
+      bn_row[c] = s1;
+      bn_row[C + c] = s2;
+    }
+  } else if (POOL) {
     // One thread per pooled cell: only the arg-max position of its 2x2 window receives gradient.  The ReLU mask is r > 0
     // (r is the rectified maximum itself) and the conv output at the arg-max was kept by build_r: no second read of z.
     // Per-cell terms of the BatchNorm sums go back to shared memory (s_D: dv, s_r: dv * zhat) and are added per channel

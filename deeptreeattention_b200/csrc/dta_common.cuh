@@ -34,6 +34,8 @@ struct ConvSrc {
   const float* k0;
   const float* k1;
   const float* k2;
+  const unsigned char* arg;   // SRC_DZ with pool = 1: `a` holds one value per POOLED cell ([B][ctot][SP*SP], SP = S/2) and `arg` the
+                              // slot (0..3) of its 2x2 window that the value belongs to -- da is zero everywhere else
   const float* gate;  // SRC_ACT: attention rows [B][G][gate_ld], gate value at gate_off + (c | p)
   int gate_ld;
   int gate_off;

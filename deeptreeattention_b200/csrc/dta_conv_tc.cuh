@@ -85,8 +85,23 @@ tc_pack_stream_kernel(ConvSrc src, int G, int B, int nchunk, size_t rows, __nv_b
         } else if (MODE == SRC_DZ) {
           const size_t base = ((size_t)b * src.ctot + ch0) * src.src_hw + p;
           float da[8], zz[8];
+          if (POOL) {
+            // compact upstream gradient of a pooled block: one value + arg-max slot per 2x2 window (3/4 of da is zero)
+            constexpr int SP = S / 2;
+            const bool in = y < 2 * SP && xx < 2 * SP;
+            const int cell = (y >> 1) * SP + (xx >> 1), slot = ((y & 1) << 1) | (xx & 1);
+            const size_t cb = ((size_t)b * src.ctot + ch0) * (SP * SP) + cell;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { da[j] = __ldg(src.a + base + (size_t)j * src.src_hw); zz[j] = __ldg(src.b + base + (size_t)j * src.src_hw); }
+            for (int j = 0; j < 8; ++j) {
+              const float v = in ? __ldg(src.a + cb + (size_t)j * (SP * SP)) : 0.f;
+              const int k = in ? (int)__ldg(src.arg + cb + (size_t)j * (SP * SP)) : -1;
+              da[j] = k == slot ? v : 0.f;
+              zz[j] = __ldg(src.b + base + (size_t)j * src.src_hw);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { da[j] = __ldg(src.a + base + (size_t)j * src.src_hw); zz[j] = __ldg(src.b + base + (size_t)j * src.src_hw); }
+          }
           const float4 k0a = __ldg(reinterpret_cast<const float4*>(src.k0 + ch0)), k0b = __ldg(reinterpret_cast<const float4*>(src.k0 + ch0) + 1);
           const float4 k1a = __ldg(reinterpret_cast<const float4*>(src.k1 + ch0)), k1b = __ldg(reinterpret_cast<const float4*>(src.k1 + ch0) + 1);
           const float4 k2a = __ldg(reinterpret_cast<const float4*>(src.k2 + ch0)), k2b = __ldg(reinterpret_cast<const float4*>(src.k2 + ch0) + 1);
