@@ -433,6 +433,10 @@ int dta_create(dta_ctx** out, int device) {
       cudaEvent_t e = nullptr;
       if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) c->sync_events.push_back(e);
     }
+    // "last CTA done" ticket counters (self-resetting, so they are zeroed exactly once): the only device memory the
+    // library owns; every per-call buffer stays the caller's
+    if (cudaMalloc(&c->tickets, 64 * sizeof(unsigned int)) == cudaSuccess) cudaMemset(c->tickets, 0, 64 * sizeof(unsigned int));
+    else c->tickets = nullptr;
     cudaGetLastError();
     cudaSetDevice(prev);
   }
@@ -447,6 +451,7 @@ void dta_destroy(dta_ctx* ctx) {
   for (cudaEvent_t e : ctx->sync_events) cudaEventDestroy(e);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
+  if (ctx->tickets) cudaFree(ctx->tickets);
   delete ctx;
 }
 
@@ -855,15 +860,13 @@ int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, c
     h.s[i] = scores[i];
     h.ds[i] = dscores ? dscores[i] : nullptr;
   }
-  double* den = static_cast<double*>(workspace);
+  if (!ctx->tickets) return fail(ctx, DTA_ERR_CUDA, "context has no ticket counters (allocation failed at dta_create)");
   float* rows = reinterpret_cast<float*>(static_cast<char*>(workspace) + 256);
   StageScope sc(ctx, "loss.cross_entropy", st);
   const long long warps = (long long)n_heads * batch;
   launch_k(ce_rows_kernel, (unsigned)((warps * 32 + 255) / 256), 256, 0, st, h, n_heads, reinterpret_cast<const long long*>(labels), class_weight, batch,
-           classes, den, rows);
+           classes, rows, loss, ctx->tickets + 0);
   DTA_CHECK_LAUNCH(ctx, "ce_rows");
-  launch_k(ce_finish_kernel, 1, 256, 0, st, rows, n_heads, batch, den, loss);
-  DTA_CHECK_LAUNCH(ctx, "ce_finish");
   return DTA_OK;
 }
 

@@ -44,6 +44,7 @@ struct dta_ctx {
   size_t ex_n4 = 0, ex_nd = 0;
   void* ex_sync = nullptr;
   int exchanged = 0;   // the last dta_backward exchanged its gradients
+  unsigned int* tickets = nullptr;      // 64 self-resetting "last CTA done" counters (allocated once at dta_create)
   const float* update_gate = nullptr;   // dta_set_update_gate: device flag that gates the BatchNorm running-statistics update
 };
 

@@ -29,16 +29,19 @@ __device__ __forceinline__ double ce_den_block(const long long* __restrict__ y, 
   return t;
 }
 
-// One warp per (head, crop): stable log-softmax, weighted NLL term and the score gradient.  Block 0 also publishes den.
+// One warp per (head, crop): stable log-softmax, weighted NLL term and the score gradient.  The CTA that finishes LAST
+// (ticket counter in context-owned memory, reset by that CTA) also sums the rows into the losses -- fixed order, fp64 -- so the
+// loss costs one launch on the step's critical path instead of two.
 __global__ void __launch_bounds__(256)
 ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restrict__ y, const float* __restrict__ w, int B, int classes,
-               double* __restrict__ den, float* __restrict__ row_loss /*[n_heads][B]*/) {
+               float* __restrict__ row_loss /*[n_heads][B]*/, float* __restrict__ loss /*[n_heads + 1]*/, unsigned int* __restrict__ ticket) {
   pdl_prologue();
   __shared__ double s_red[8];
+  __shared__ double s_head[8];
+  __shared__ unsigned int s_last;
   const double dsum = ce_den_block(y, w, B, classes, s_red);
-  if (blockIdx.x == 0 && threadIdx.x == 0) den[0] = dsum;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (gw >= n_heads * B) return;
+  if (gw < n_heads * B) {
   const int head = gw / B, b = gw - head * B;
   const float* s = h.s[head] + (size_t)b * classes;
   float m = -INFINITY;
@@ -61,21 +64,22 @@ ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restrict__ y, const f
       ds[(size_t)b * classes + c] = wy * inv * (p - (c == yc ? 1.f : 0.f));
     }
   }
-}
-
-// loss[head] = sum_b row_loss / den (fp64, fixed order), loss[n_heads] = sum over heads.  One block, one warp per head.
-__global__ void __launch_bounds__(256)
-ce_finish_kernel(const float* __restrict__ row_loss, int n_heads, int B, const double* __restrict__ den, float* __restrict__ loss) {
-  pdl_prologue();
-  __shared__ double s_head[8];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  }
+  // ---- last CTA: loss[head] = sum_b row_loss / den (fp64, fixed order), loss[n_heads] = sum over heads ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int warp = threadIdx.x >> 5;
   if (warp < n_heads) {
     double a = 0.0;
 #pragma unroll 4
-    for (int b = lane; b < B; b += 32) a += (double)__ldg(row_loss + (size_t)warp * B + b);
+    for (int b = lane; b < B; b += 32) a += (double)__ldcg(row_loss + (size_t)warp * B + b);
     a = warp_sum(a);
     if (lane == 0) {
-      const double v = a / den[0];
+      const double v = a / dsum;
       loss[warp] = (float)v;
       s_head[warp] = v;
     }
@@ -85,6 +89,7 @@ ce_finish_kernel(const float* __restrict__ row_loss, int n_heads, int B, const d
     double total = 0.0;
     for (int hd = 0; hd < n_heads; ++hd) total += s_head[hd];
     loss[n_heads] = (float)total;
+    *ticket = 0u;
   }
 }
 
