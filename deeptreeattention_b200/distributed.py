@@ -177,7 +177,7 @@ class _PeerBuffers:
         module.__dict__["_grad_buffers"] = (self.flat, self.alpha)
         # Optional (DTA_EXCHANGE_IN_BACKWARD=1): the backward pass exchanges its gradients itself in two launches, everything but
         # conv1's weights under conv1's weight-gradient kernel.  Measured SLOWER than the single exchange kernel after the
-        # backward pass (N = 2: 1.057 vs 1.033 ms per step, N = 8: 1.089 vs 1.035 ms; profiles/r05f_*): the spinning exchange CTAs
+        # backward pass (N = 2: 1.057 vs 1.033 ms per step, N = 8: 1.011 vs 0.972 ms; profiles/r06y_*): the spinning exchange CTAs
         # take issue slots from the tensor kernel they hide under.  Off by default.
         self.in_backward = False
         if self.multicast_ptr and os.environ.get("DTA_EXCHANGE_IN_BACKWARD", "0") == "1":
