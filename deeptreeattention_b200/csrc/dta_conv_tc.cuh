@@ -15,6 +15,7 @@
 // (forward: row = M) or MN-major (wgrad: row = K), and (c) a tap is `start address += s * 16 B`
 // (dta_tc.cuh; verified on hardware by tools/tc_probe.cu).
 #pragma once
+#include <type_traits>
 #include "dta_common.cuh"
 #include "dta_tc.cuh"
 
@@ -242,6 +243,10 @@ struct TcFprop {
 // also emit the packed position stream to global memory for the weight-gradient kernel -- the separate pack pass over
 // the crops (183 MB read + 227 MB written) disappears into this kernel's shadow.
 constexpr int kTcConvWarps = 8;
+#ifndef DTA_X_PREFETCH
+#define DTA_X_PREFETCH 2
+#endif
+constexpr int kXPrefetch = DTA_X_PREFETCH;   // stages the producer warp's L2 prefetch of the raw crops runs ahead (0 = off)
 struct FuseX {
   const float* x;             // crops (B, bands, S, S) float32
   int bands;
@@ -259,9 +264,13 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
   using St = Stream<S>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  __shared__ uint64_t full_bar[4], empty_bar[4], tmem_full[2], tmem_empty[2];
+  // Accumulator hand-off.  ACC2: one full / empty barrier pair per accumulator stage.  !ACC2 (conv1, one accumulator of SUB
+  // subtiles): one pair per SUBTILE -- the issuer signals subtile s as soon as its last MMA is queued and re-enters it for the
+  // next tile as soon as it is drained, so the bubble between two tiles is one subtile's drain instead of the whole epilogue.
+  constexpr int NHB = ACC2 ? 2 : Cfg::SUB;
+  __shared__ uint64_t full_bar[4], empty_bar[4], tmem_full[NHB], tmem_empty[NHB];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[2][NCO];
+  __shared__ __align__(16) float s_bias[2][NCO];   // per group (G <= 2), filled once: no per-tile barrier in the epilogue
 
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -273,10 +282,16 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
       tc::mbar_init(&full_bar[i], FUSEX ? 1 + 32 * kTcConvWarps : 1);   // W bulk copy (+ every converter thread)
       tc::mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 8); }
+    for (int i = 0; i < NHB; ++i) { tc::mbar_init(&tmem_full[i], 1); tc::mbar_init(&tmem_empty[i], 8); }
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc(&tmem_base_s, 512);
+  const bool has_bias = bias.p[0] != nullptr;
+  for (int i = tid; i < 2 * NCO; i += blockDim.x) {
+    const int g = i / NCO, n = i - g * NCO;
+    const int chg = g * cout_g + n;
+    s_bias[g][n] = (has_bias && g < G && n < cout_g) ? __ldg(bias.p[chg / bias_split] + (chg % bias_split)) : 0.f;
+  }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -285,12 +300,40 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
 
   if (warp == 0) {
     // ---------------- producer: bulk copies global -> shared ----------------
-    if (elect_one_sync()) {
-      uint32_t it = 0;
-      for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
-        const int g = work / ntiles, tile = work - g * ntiles;
-        const size_t row0 = (size_t)tile * Cfg::TILE;       // first staged row (= GUARD + q0 - GUARD)
-        for (int ks = 0; ks < nstage; ++ks, ++it) {
+    // FUSEX: the whole warp also prefetches the raw crops of the stage kXPrefetch steps ahead into L2 (one elected lane still
+    // owns the barrier and the bulk copy of the weights).  The converter warps hold one stage of loads in registers at a
+    // time, so their period is load latency + conversion; with the lines already in L2 that latency drops from a DRAM to an
+    // L2 round trip and the MMAs stop waiting for operands.
+    const uint32_t leader = elect_one_sync();
+    auto prefetch_x = [&](int work, int ks) {
+      if constexpr (FUSEX && kXPrefetch > 0) {
+      while (ks >= nstage) { ks -= nstage; work += gridDim.x; }
+      if (work >= nwork) return;
+      const long long q0 = (long long)work * Cfg::TILE - kTcGuard, q1 = q0 + Cfg::AROWS;   // stream positions staged (FUSEX: one group)
+      const int b_lo = (int)(q0 > 0 ? q0 / St::PC : 0);
+      const int b_hi = (int)min((long long)B - 1, (q1 - 1) / St::PC);
+      const int ch0 = ks * 16;
+      const int nch = min(16, fx.bands - ch0);
+      if (nch <= 0) return;
+      const uintptr_t xbase = reinterpret_cast<uintptr_t>(fx.x);
+      for (int b = b_lo; b <= b_hi; ++b) {
+        const uintptr_t beg = xbase + ((size_t)b * fx.bands + ch0) * (S * S) * sizeof(float);
+        const uintptr_t end = beg + (size_t)nch * (S * S) * sizeof(float);
+        uintptr_t a = (beg & ~uintptr_t(127));
+        if (a < xbase) a = xbase;
+        for (a += (uintptr_t)lane * 128; a < end; a += 32 * 128) asm volatile("prefetch.global.L2 [%0];" : : "l"(a));
+      }
+      }
+    };
+    if (FUSEX)
+      for (int ks = 1; ks < kXPrefetch; ++ks) prefetch_x(blockIdx.x, ks);
+    uint32_t it = 0;
+    for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+      const int g = work / ntiles, tile = work - g * ntiles;
+      const size_t row0 = (size_t)tile * Cfg::TILE;       // first staged row (= GUARD + q0 - GUARD)
+      for (int ks = 0; ks < nstage; ++ks, ++it) {
+        if (FUSEX) prefetch_x(work, ks + kXPrefetch);
+        if (leader) {
           const int st = it % Cfg::NSTAGE;
           const uint32_t ph = (it / Cfg::NSTAGE) & 1;
           tc::mbar_wait(&empty_bar[st], ph ^ 1);
@@ -307,6 +350,7 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
           }
           tc::bulk_g2s(sa + Cfg::A_BYTES, wp + ((size_t)g * nstage + ks) * (Cfg::W_BYTES / 2), Cfg::W_BYTES, &full_bar[st]);
         }
+        if (FUSEX) __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -317,8 +361,10 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
     uint32_t it = 0, tile_it = 0;
     for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++tile_it) {
       const uint32_t acc = tile_it % Cfg::NACC, acc_use = tile_it / Cfg::NACC;
-      tc::mbar_wait(&tmem_empty[acc], (acc_use & 1) ^ 1);
-      tc::fence_after_sync();
+      if (ACC2) {
+        tc::mbar_wait(&tmem_empty[acc], (acc_use & 1) ^ 1);
+        tc::fence_after_sync();
+      }
       const uint32_t dbase = tmem + acc * Cfg::ACC_COLS;
       for (int ks = 0; ks < nstage; ++ks, ++it) {
         const int st = it % Cfg::NSTAGE;
@@ -334,6 +380,10 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
         const uint32_t b_lo32 = (uint32_t)b_d, b_hi32 = (uint32_t)(b_d >> 32);
 #pragma unroll
         for (int s = 0; s < Cfg::SUB; ++s) {
+          if (!ACC2 && ks == 0) {             // subtile s of the previous tile must have been drained
+            tc::mbar_wait(&tmem_empty[s], (tile_it & 1) ^ 1);
+            tc::fence_after_sync();
+          }
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const int shift = kTcGuard + s * 128 + (t / 3 - 1) * St::PT + (t % 3 - 1);   // rows == 16-byte units
@@ -344,11 +394,15 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
               tc::mma_bf16(dbase + s * (2 * NCO), desc_from(al_lo32 + shift, a_hi32), desc_from(b_lo32 + boff, b_hi32), idesc2, 1u);
             }
           }
+          if (!ACC2 && ks == nstage - 1) {    // subtile s is complete once everything issued so far has run
+            __syncwarp();
+            if (leader) tc::mma_commit(&tmem_full[s]);
+          }
         }
         __syncwarp();
         if (leader) tc::mma_commit(&empty_bar[st]);
       }
-      if (leader) tc::mma_commit(&tmem_full[acc]);
+      if (ACC2 && leader) tc::mma_commit(&tmem_full[acc]);
       __syncwarp();
     }
   } else if (FUSEX && warp >= 10) {
@@ -423,7 +477,6 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
     const int ew = warp - 2;                   // 0..7
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int chalf = ew >> 2;                 // which half of the output channels
-    const int et = tid - 64;                   // 0..255
     constexpr int CH_PER = NCO / 2;
     constexpr int NGRP = (CH_PER + 31) / 32;   // 32-channel groups per thread (lane l ends up owning channel 32*grp + l)
     float run_sum[2][NGRP], run_sq[2][NGRP];
@@ -480,52 +533,80 @@ tc_conv_fprop_kernel(const __nv_bfloat16* __restrict__ xp /*[2][nchunk][rows][8]
       if (stats != nullptr && g != cur_g && cur_g >= 0) flush_stats(cur_g);
       cur_g = g;
       const uint32_t acc = tile_it % Cfg::NACC, acc_use = tile_it / Cfg::NACC;
-      float* sb = s_bias[tile_it & 1];
-      if (et < NCO) {
-        float bv = 0.f;
-        const int chg = g * cout_g + et;
-        if (et < cout_g && bias.p[0] != nullptr) bv = __ldg(bias.p[chg / bias_split] + (chg % bias_split));
-        sb[et] = bv;
+      const float* sb = s_bias[g & 1];
+      if (ACC2) {
+        tc::mbar_wait(&tmem_full[acc], acc_use & 1);
+        tc::fence_after_sync();
       }
-      asm volatile("bar.sync 1, 256;" : : : "memory");
-      tc::mbar_wait(&tmem_full[acc], acc_use & 1);
-      tc::fence_after_sync();
+      constexpr int NCC = GW / 16;                 // 16-channel blocks per group
+      constexpr int NIT = Cfg::SUB * NCC;          // (subtile, 16-channel block) steps per group, walked two at a time
+      constexpr int CCB = NCC == 2 ? 16 : 0;       // channel offset of the odd steps
+      static_assert(NIT % 2 == 0 && (NCC == 1 || NCC == 2), "the epilogue walks its steps in pairs");
+      static_assert(ACC2 || (NGRP == 1 && NCC == 2), "per-subtile hand-off: one step pair per subtile");
+      const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + acc * Cfg::ACC_COLS;
 #pragma unroll
       for (int grp = 0; grp < NGRP; ++grp) {
         const int cg0 = chalf * CH_PER + grp * 32;
-#pragma unroll 1
-        for (int s = 0; s < Cfg::SUB; ++s) {
+        const bool live = cg0 < cout_g;            // warp-uniform: this warp's channels exist
+        auto issue = [&](int k, int cc, float* v0, float* v1) {
+          const int s = k / NCC;
+          const uint32_t taddr = tbase + s * (2 * NCO) + cg0 + cc;
+          tc::tmem_ld16(taddr, v0);
+          tc::tmem_ld16(taddr + NCO, v1);
+        };
+        auto process = [&](int k, auto ccv, const float* v0, const float* v1) {
+          constexpr int cc = decltype(ccv)::value;
+          const int s = k / NCC;
+          const int c0 = cg0 + cc;
           const long long q = (long long)tile * Cfg::TILE + s * 128 + quad * 32 + lane;
           const int b = (int)(q / St::PC);
           const int r = (int)(q - (long long)b * St::PC);
           const int yy = r / St::PT, xx = r - yy * St::PT;
           const bool valid = b < B && yy >= 1 && xx < S;
-          float* orow = out + ((size_t)b * out_ctot + (size_t)g * cout_g) * (S * S) + (yy - 1) * S + xx;
-          const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + acc * Cfg::ACC_COLS + s * (2 * NCO);
+          if (valid && c0 < cout_g) {
+            float* orow = out + ((size_t)b * out_ctot + (size_t)g * cout_g + c0) * (S * S) + (yy - 1) * S + xx;
+            float bs[16];
 #pragma unroll
-          for (int cc = 0; cc < GW; cc += 16) {
-            const int c0 = cg0 + cc;
-            if (c0 < cout_g) {
-              float v0[16], v1[16];
-              tc::tmem_ld16(taddr + c0, v0);
-              tc::tmem_ld16(taddr + NCO + c0, v1);
-              tc::tmem_ld_wait();
-              if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float o = v0[j] + v1[j] + sb[c0 + j];
-                  orow[(size_t)(c0 + j) * (S * S)] = o;
-                  ps[grp][cc + j] += o;
-                  pq[grp][cc + j] = fmaf(o, o, pq[grp][cc + j]);
-                }
-              }
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(sb + c0 + j);
+              bs[j] = b4.x; bs[j + 1] = b4.y; bs[j + 2] = b4.z; bs[j + 3] = b4.w;
             }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float o = v0[j] + v1[j] + bs[j];
+              orow[(size_t)j * (S * S)] = o;
+              ps[grp][cc + j] += o;
+              pq[grp][cc + j] = fmaf(o, o, pq[grp][cc + j]);
+            }
+          }
+        };
+        float va0[16], va1[16];
+#pragma unroll 1
+        for (int k = 0; k < NIT; k += 2) {
+          if (!ACC2) {                             // one pair of steps = one subtile
+            tc::mbar_wait(&tmem_full[k / 2], tile_it & 1);
+            tc::fence_after_sync();
+          }
+          if (live) {
+            issue(k, 0, va0, va1);
+            tc::tmem_ld_wait();
+            process(k, std::integral_constant<int, 0>{}, va0, va1);
+            issue(k + 1, CCB, va0, va1);
+            tc::tmem_ld_wait();
+            process(k + 1, std::integral_constant<int, CCB>{}, va0, va1);
+          }
+          if (!ACC2) {
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[k / 2]);
           }
         }
       }
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+      if (ACC2) {
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
+      }
     }
     if (stats != nullptr && cur_g >= 0) flush_stats(cur_g);
     if (stats != nullptr) {

@@ -280,6 +280,37 @@ def test_side_stream_overlap_is_bit_identical(kind, bands, classes, batch):
             assert torch.equal(b, other[4][k]), k
 
 
+@pytest.mark.parametrize("kind,bands,classes,batch", [("hang2020", 369, 50, 40), ("spectral", 30, 7, 5), ("spatial", 3, 4, 9), ("hang2020", 349, 6, 1100)])
+def test_conv1_crop_conversion_variants_agree(kind, bands, classes, batch):
+    """Option "fuse_x": who converts the raw fp32 crops into conv1's split-bf16 operand (0 = a pack kernel in front, 1 = eight
+    converter warps inside the convolution, the default).  The operand and the MMA order are the same, so conv1's output --
+    hence everything downstream -- is the same: scores within 2e-6, gradients within 1e-5 relative L2, and the default
+    matches the oracle."""
+    from deeptreeattention_b200 import _capi
+    table = orc.init_params(kind, bands, classes, 23, perturb_bn=True)
+    x, y = orc.make_inputs(batch, bands, classes, 23)
+    dev = torch.cuda.current_device()
+    runs = {}
+    try:
+        for fx in (1, 0):
+            _capi.set_option(dev, "fuse_x", fx)
+            runs[fx] = run_cuda(kind, bands, classes, table, x, y, "R2", True)
+    finally:
+        _capi.set_option(dev, "fuse_x", 1)
+    for fx in (0,):
+        assert abs(runs[fx][0] - runs[1][0]) <= 2e-6 * max(1.0, abs(runs[1][0]))
+        np.testing.assert_allclose(runs[fx][1], runs[1][1], rtol=0, atol=2e-6)
+        for k, g in runs[1][3].items():
+            if g is not None:
+                # a different BatchNorm partial-sum order moves the statistics in the last bit; at a large batch that can flip
+                # a ReLU / max-pool decision somewhere (DESIGN section 2), hence the relative-L2 form of the bound
+                num, den = (runs[fx][3][k].double() - g.double()).norm().item(), g.double().norm().item()
+                assert num <= (1e-5 if batch <= 64 else 2e-3) * den + 1e-9, (fx, k, num, den)
+    if batch <= 64:
+        loss_ref, res_ref, heads_ref, _, _ = orc.step(kind, table, x, y, regime="R2", training=True)
+        assert abs(runs[1][0] - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
+
+
 def test_year_ensemble_matches_oracle_and_skips_zero_years():
     """learned_ensemble (src/models/year.py:9-33; shapes of tests/test_year.py): mean of the last heads of the
     non-zero years, each year network checked against the oracle."""
