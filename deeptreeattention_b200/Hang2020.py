@@ -180,13 +180,17 @@ class _FusedNetFunction(torch.autograd.Function):
                 accumulating = not persistent
             else:
                 accumulating = False
+            # dta_backward writes EVERY gradient of the table (kernels for the reached ones, its own zero-fill for dead Conv1d
+            # taps and unreached heads, on its side stream), so the buffers need no zero-fill in front of it: two fill kernels
+            # less on the step's critical path.  _capi.POISON_GRADS (tests) fills them with NaN to prove that coverage.
             if persistent:
                 flat, galpha = bufs
-                flat.zero_()
-                galpha.zero_()
             else:
-                flat = torch.zeros(sum(numels), dtype=torch.float32, device=dev)
-                galpha = torch.zeros((), dtype=torch.float64, device=dev)
+                flat = torch.empty(sum(numels), dtype=torch.float32, device=dev)
+                galpha = torch.empty((), dtype=torch.float64, device=dev)
+            if _capi.POISON_GRADS:
+                flat.fill_(float("nan"))
+                galpha.fill_(float("nan"))
             grads, off = [], 0
             for p, n in zip(params, numels):
                 if p.dtype == torch.float32:

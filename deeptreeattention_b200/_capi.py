@@ -254,6 +254,9 @@ def saved_region(net_kind: int, batch: int, bands: int, classes: int, training: 
 # Diagnostics (parity tests): when True, every fused forward leaves a reference to its ``saved`` buffer in the module's
 # spec (``model.fused_spec().last_saved``) so that the convolution outputs can be read back with ``saved_region``.
 KEEP_SAVED = False
+# tests: the gradient buffers handed to dta_backward are pre-filled with NaN (default: left uninitialised -- the library writes all
+# of them), so a gradient the library failed to write shows up as NaN.  Also switched on by the environment variable DTA_POISON_GRADS=1.
+POISON_GRADS = os.environ.get("DTA_POISON_GRADS", "0") == "1"
 
 
 def set_update_gate(device_index: int, flag_ptr):

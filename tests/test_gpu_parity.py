@@ -311,6 +311,42 @@ def test_conv1_crop_conversion_variants_agree(kind, bands, classes, batch):
         assert abs(runs[1][0] - loss_ref.item()) <= 1e-4 * abs(loss_ref.item())
 
 
+@pytest.mark.parametrize("kind,regime,training", [("hang2020", "R1", True), ("hang2020", "R2", True), ("hang2020", "R2", False),
+                                                  ("spectral", "R2", True), ("spectral", "R1", True), ("spatial", "R2", True),
+                                                  ("spatial", "R1", False), ("vanilla", "R1", True)])
+def test_backward_writes_every_gradient(kind, regime, training):
+    """The gradient buffers are handed to dta_backward uninitialised (no zero-fill kernels in front of the backward pass): the
+    library must write every element itself -- kernels for the reached parameters, its own zero-fill for the dead Conv1d taps
+    and for heads no loss term reaches.  Proved by poisoning the buffers with NaN first: none may survive, and the gradients
+    equal the unpoisoned run bit for bit."""
+    from deeptreeattention_b200 import _capi
+    bands, classes, batch = 30, 7, 6
+    table = orc.init_params(kind, bands, classes, 31, perturb_bn=True)
+    x, y = orc.make_inputs(batch, bands, classes, 31)
+    plain = run_cuda(kind, bands, classes, table, x, y, regime, training)
+    _capi.POISON_GRADS = True
+    try:
+        m = _modules()[kind](bands, classes)
+        m.load_state_dict(table)
+        m = m.cuda().train(training)
+        out = m(x.cuda())
+        heads = m.head_scores if kind == "hang2020" else ([out] if kind == "vanilla" else out)
+        loss = orc.loss_regime(regime, out, heads, y.cuda())
+        loss.backward()
+        torch.cuda.synchronize()
+        spec = m.fused_spec()
+        assert not torch.isnan(spec.flat_grad).any(), "dta_backward left part of the flat gradient buffer unwritten"
+        if spec.alpha_grad is not None:
+            assert not torch.isnan(spec.alpha_grad).any()
+        for k, p in m.named_parameters():
+            g = plain[3][k]
+            assert (p.grad is None) == (g is None), k
+            if g is not None:
+                assert torch.equal(p.grad.cpu(), g), k
+    finally:
+        _capi.POISON_GRADS = False
+
+
 def test_year_ensemble_matches_oracle_and_skips_zero_years():
     """learned_ensemble (src/models/year.py:9-33; shapes of tests/test_year.py): mean of the last heads of the
     non-zero years, each year network checked against the oracle."""
