@@ -196,7 +196,6 @@ struct BwdWork {
                            // gradient may still read its stream on the side stream while block k-1's is being packed)
   __nv_bfloat16* wdp[2];   // packed input-gradient weights of conv2, conv3 (tensor-core path)
   float* rpart;            // partial tiles of the batched small-gradient reduction
-  double* bnpart;          // group partials of the BatchNorm-backward finalize run inside the attention kernels (option "bn_fuse")
   size_t bytes;
 };
 BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
@@ -230,7 +229,6 @@ BwdWork layout_bwd(const dta_shape& s, const NetDesc& d, void* base) {
   W.wd[0] = c.take((size_t)d.nb * 32 * 9 * s.bands);
   W.wd[1] = c.take((size_t)d.nb * 64 * 9 * 32);
   W.wd[2] = c.take((size_t)d.nb * 128 * 9 * 64);
-  W.bnpart = reinterpret_cast<double*>(c.take((size_t)2 * kBnFuseMaxGroups * d.nb * 256));   // doubles; offsets are 256-byte aligned
   W.bytes = c.off;
   return W;
 }
@@ -438,7 +436,7 @@ int dta_create(dta_ctx** out, int device) {
     }
     // "last CTA done" ticket counters (self-resetting, so they are zeroed exactly once): the only device memory the
     // library owns; every per-call buffer stays the caller's
-    if (cudaMalloc(&c->tickets, 256 * sizeof(unsigned int)) == cudaSuccess) cudaMemset(c->tickets, 0, 256 * sizeof(unsigned int));
+    if (cudaMalloc(&c->tickets, 64 * sizeof(unsigned int)) == cudaSuccess) cudaMemset(c->tickets, 0, 64 * sizeof(unsigned int));
     else c->tickets = nullptr;
     cudaGetLastError();
     cudaSetDevice(prev);
@@ -488,10 +486,6 @@ int dta_set_option(dta_ctx* ctx, const char* key, int64_t value) {
     ctx->profile = value != 0;
     return DTA_OK;
   }
-  if (!strcmp(key, "bn_fuse")) {
-    ctx->bn_fuse = value != 0;
-    return DTA_OK;
-  }
   if (!strcmp(key, "fuse_x")) {
     ctx->fuse_x = value != 0;
     return DTA_OK;
@@ -524,7 +518,6 @@ int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value) {
   if (!strcmp(key, "overlap")) { *value = ctx->overlap; return DTA_OK; }
   if (!strcmp(key, "pdl")) { *value = ctx->pdl; return DTA_OK; }
   if (!strcmp(key, "fuse_x")) { *value = ctx->fuse_x; return DTA_OK; }
-  if (!strcmp(key, "bn_fuse")) { *value = ctx->bn_fuse; return DTA_OK; }
   if (!strcmp(key, "exchanged")) { *value = ctx->exchanged; return DTA_OK; }
   return DTA_ERR_INVALID_ARG;
 }
@@ -998,26 +991,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     }
     return g;
   };
-  // BatchNorm-backward finalize inside the attention-backward kernel (its last CTAs; option "bn_fuse") or as its own launch
-  const bool bn_fused = ctx->bn_fuse && ctx->tickets != nullptr;
-  auto bn_fuse_args = [&](int k) {
-    BnBwdFuse f{};
-    if (!bn_fused) return f;
-    int ngroups = (B + 31) / 32;
-    if (ngroups > kBnFuseMaxGroups) ngroups = kBnFuseMaxGroups;
-    f.grp = (B + ngroups - 1) / ngroups;
-    f.ngroups = (B + f.grp - 1) / f.grp;
-    f.part = W.bnpart;
-    f.tickets = ctx->tickets + kBnFuseTicket0;
-    f.count = (double)B * kHWpre[k];
-    f.training = shape->training;
-    f.bn = bn_params(params, d, k);
-    f.gr = bn_grads(k);
-    f.k0 = W.k0[k]; f.k1 = W.k1[k]; f.k2 = W.k2[k];
-    return f;
-  };
   auto bn_bwd = [&](int k) -> int {
-    if (bn_fused) return DTA_OK;
     StageScope sc(ctx, "bwd.bn_finalize", st);
     const int ctot = nb * kC[k];
     launch_k(bn_bwd_finalize_kernel, (ctot + kBnCh - 1) / kBnCh, kBnCh * kBnSlices, 0, st, W.bnrows, B, nb, kC[k], (double)B * kHWpre[k], bn_params(params, d, k),
@@ -1104,7 +1078,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn3", st);
     launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[2], L.bn_scale[2], L.bn_shift[2], L.bn_mean[2], L.bn_istd[2], attn_prm(2), classes, L.att[2], L.feat[2],
-                                              ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow[2], tcp ? 1 : 0, bn_fuse_args(2));
+                                              ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow[2], tcp ? 1 : 0);
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<3>");
     if ((rc = attn_param_grads(2)) != DTA_OK) return rc;
@@ -1143,7 +1117,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn2", st);
     launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[1], L.bn_scale[1], L.bn_shift[1], L.bn_mean[1], L.bn_istd[1], attn_prm(1), classes, L.att[1], L.feat[1],
-                                              ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow[1], tcp ? 1 : 0, bn_fuse_args(1));
+                                              ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow[1], tcp ? 1 : 0);
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<2>");
     if ((rc = attn_param_grads(1)) != DTA_OK) return rc;
@@ -1181,7 +1155,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn1", st);
     launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[0], L.bn_scale[0], L.bn_shift[0], L.bn_mean[0], L.bn_istd[0], attn_prm(0), classes, L.att[0], L.feat[0],
-                                              ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow[0], 0, bn_fuse_args(0));
+                                              ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow[0], 0);
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<1>");
     if ((rc = attn_param_grads(0)) != DTA_OK) return rc;

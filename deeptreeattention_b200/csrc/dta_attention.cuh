@@ -4,7 +4,6 @@
 // spectral_attention.forward :149-168, spatial_attention.forward :105-124, Classifier :63-66.
 #pragma once
 #include "dta_common.cuh"
-#include "dta_misc.cuh"
 #include "dta_tc.cuh"
 
 namespace dta {
@@ -380,8 +379,7 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
                 const float* __restrict__ att, const float* __restrict__ feat_unused,
                 Ptr2 dscores /*per branch [B][classes] or null*/, const float* __restrict__ dout /*[B][G][C][HW] or null*/,
                 float* __restrict__ da /*[B][G*C][HWPRE]; compact: [B][G*C][HW] values, then [B][G*C][HW] arg-max bytes*/,
-                float* __restrict__ bnrow /*[B][G][2C]*/, float* __restrict__ prow /*[B][G][ROW_LD]*/, int compact,
-                const __grid_constant__ BnBwdFuse bnf /*part != null: the last CTAs also run the BatchNorm-backward finalize*/) {
+                float* __restrict__ bnrow /*[B][G][2C]*/, float* __restrict__ prow /*[B][G][ROW_LD]*/, int compact) {
   pdl_prologue();
   using Cfg = AttnCfg<C, SPRE, POOL>;
   using Row = AttnBwdRow<C, SPRE, POOL>;
@@ -677,7 +675,6 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
       if (lane == 0) { bn_row[c] = s1; bn_row[C + c] = s2; }
     }
   }
-  if (bnf.part != nullptr) bn_bwd_fused_finalize<C>(bnf, bnrow, mean, istd);
 }
 
 template <int C, int SPRE, bool POOL>

@@ -23,7 +23,6 @@ struct dta_ctx {
   long long launches_total = 0;   // ... by all earlier calls on this context (option "launches_total" = both)
   int profile = 0;
   int fuse_x = 1;      // conv1 forward converts the raw crops itself (no separate pack pass); 0 = pack kernel + pre-packed operand
-  int bn_fuse = 1;     // BatchNorm-backward finalize by the last CTAs of the attention-backward kernel (no launch of its own); 0 = bn_bwd_finalize_kernel
   std::vector<std::string> stage_names;
   std::vector<double> stage_ms;
   std::vector<long long> stage_calls;
@@ -45,7 +44,7 @@ struct dta_ctx {
   size_t ex_n4 = 0, ex_nd = 0;
   void* ex_sync = nullptr;
   int exchanged = 0;   // the last dta_backward exchanged its gradients
-  unsigned int* tickets = nullptr;      // 256 self-resetting "last CTA done" counters (allocated once at dta_create)
+  unsigned int* tickets = nullptr;      // 64 self-resetting "last CTA done" counters (allocated once at dta_create)
   const float* update_gate = nullptr;   // dta_set_update_gate: device flag that gates the BatchNorm running-statistics update
 };
 

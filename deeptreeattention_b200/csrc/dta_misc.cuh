@@ -191,89 +191,6 @@ bn_bwd_finalize_kernel(const float* __restrict__ rows, int B, int G, int C, doub
   if (gr.dconv_b[br]) gr.dconv_b[br][cb] = (float)dbias;
 }
 
-// ---------------------------------------------------------------------------------------
-// The same finalize WITHOUT a launch of its own (option "bn_fuse", default): the attention-backward CTAs that finish last do
-// it.  Crops are split into `ngroups` groups of `grp`; the CTA that completes a group (ticket counter per group) adds that
-// group's rows in crop order (fp64) into part[group][G*2C]; the CTA that completes the last group (one more ticket) adds the
-// group partials in group order and emits the coefficients and dgamma / dbeta / dbias exactly like bn_bwd_finalize_kernel.
-// The order of every sum is fixed by the data layout, not by which CTA happens to be last: results are run-to-run identical.
-// Tickets live in context-owned memory, zero on entry and reset by the CTA that consumes them.
-// ---------------------------------------------------------------------------------------
-constexpr int kBnFuseMaxGroups = 64;
-constexpr int kBnFuseTicket0 = 64;     // first of the kBnFuseMaxGroups + 1 context ticket counters used here (0 belongs to the loss)
-struct BnBwdFuse {
-  double* part;            // [ngroups][G*2C]; nullptr = not fused (bn_bwd_finalize_kernel is launched instead)
-  unsigned int* tickets;   // [ngroups + 1]
-  int grp, ngroups;
-  double count;
-  int training;
-  BnParams bn;
-  BnGrads gr;
-  float* k0; float* k1; float* k2;
-};
-
-// Called by every thread of every CTA of the attention-backward grid (blockIdx.x = crop, blockIdx.y = branch) after the CTA's
-// row of `rows` has been written.
-template <int C>
-__device__ __forceinline__ void bn_bwd_fused_finalize(const BnBwdFuse& f, const float* rows /*[B][G][2C]*/, const float* __restrict__ mean,
-                                                      const float* __restrict__ istd) {
-  __shared__ unsigned int s_last;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int B = gridDim.x, G = gridDim.y;
-  const int gi = blockIdx.x / f.grp;
-  const int b0 = gi * f.grp, b1 = min(B, b0 + f.grp);
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) s_last = atomicAdd(f.tickets + gi, 1u) == (unsigned)((b1 - b0) * G - 1) ? 1u : 0u;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int ncol = G * 2 * C;
-  for (int j = tid; j < ncol; j += nt) {
-    double a = 0.0;
-#pragma unroll 8
-    for (int b = b0; b < b1; ++b) a += (double)__ldcg(rows + (size_t)b * ncol + j);
-    f.part[(size_t)gi * ncol + j] = a;
-  }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    f.tickets[gi] = 0u;
-    s_last = atomicAdd(f.tickets + f.ngroups, 1u) == (unsigned)(f.ngroups - 1) ? 1u : 0u;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int ch = tid; ch < G * C; ch += nt) {
-    const int g = ch / C, c = ch - g * C;
-    double s1 = 0.0, s2 = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < f.ngroups; ++k) {
-      s1 += __ldcg(f.part + (size_t)k * ncol + g * 2 * C + c);
-      s2 += __ldcg(f.part + (size_t)k * ncol + g * 2 * C + C + c);
-    }
-    const int br = ch / f.bn.c_per_branch, cb = ch - br * f.bn.c_per_branch;
-    const double gam = f.bn.gamma[br][cb];
-    const double is = istd[ch], mu = mean[ch];
-    const double a = gam * is;
-    double b1c = 0.0, b2c = 0.0, dbias;
-    if (f.training) {
-      b1c = -a * is * s2 / f.count;
-      b2c = -a * s1 / f.count - b1c * mu;
-      dbias = 0.0;  // sum of dz over the batch vanishes identically under batch statistics
-    } else {
-      dbias = a * s1;
-    }
-    f.k0[ch] = (float)a;
-    f.k1[ch] = (float)b1c;
-    f.k2[ch] = (float)b2c;
-    if (f.gr.dgamma[br]) f.gr.dgamma[br][cb] = (float)s2;
-    if (f.gr.dbeta[br]) f.gr.dbeta[br][cb] = (float)s1;
-    if (f.gr.dconv_b[br]) f.gr.dconv_b[br][cb] = (float)dbias;
-  }
-  if (tid == 0) f.tickets[f.ngroups] = 0u;
-}
-
 // out[j*ostride] = sum_b rows[b*ld + j], j < n.  Block = 32 columns x 8 batch slices.
 __global__ void colsum_kernel(const float* __restrict__ rows, size_t ld, int B, int n, float* __restrict__ out,
                               int ostride) {

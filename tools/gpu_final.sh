@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence run on ONE GPU: parity tests, smoke, bench lines (graph / eager / cfg2 / cfg5 / reference arm), ncu launch
 # list, ncu --set full of the dominant kernels.  Usage: gpurun -- 'bash tools/gpu_final.sh tag'
-TAG=${1:-r05z}
+TAG=${1:-r07z}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/${TAG}_gpu.txt
 timeout 700 python -m pytest tests -m gpu -q --timeout=300 > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log
@@ -31,3 +31,4 @@ timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --c
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu --graph 0 --sustain 0"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_conv_wgrad_kernel -s 8 -c 3 -f -o gpurun_out/${TAG}_prof_wgrad $CMD > gpurun_out/${TAG}_prof.log 2>&1; echo "wgrad rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_conv_fprop_kernel -s 20 -c 5 -f -o gpurun_out/${TAG}_prof_fprop $CMD >> gpurun_out/${TAG}_prof.log 2>&1; echo "fprop rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_ -s 12 -c 6 -f -o gpurun_out/${TAG}_prof_attn $CMD >> gpurun_out/${TAG}_prof.log 2>&1; echo "attn rc=$?"
