@@ -437,19 +437,35 @@ def run_b200(args):
         # the library's fused weighted cross-entropy (== sum of F.cross_entropy over the heads, tests/test_gpu_parity.py)
         return cross_entropy_heads(heads_of(m, out), y)
 
-    def train_step(xd, yd=None):
-        for p in params:
-            p.grad = None
-        loss = loss_fn(model, model(xd), y_dev if yd is None else yd)
-        loss.backward()
-        sync.sync()
-        return loss
+    # --step fused (default where the loss is the sum over the network's own heads: cfg3 / R2, cfg2): the whole step is ONE
+    # library call, train.fused_train_step -> dta_train_step (bit-identical to the three-call sequence below,
+    # tests/test_train_step.py); --step autograd: model(x) -> cross_entropy_heads -> loss.backward() through torch.autograd.
+    fused_ok = (args.config == "cfg3" and args.regime == "R2") or args.config == "cfg2"
+    use_fused = args.step == "fused" and fused_ok
+    if use_fused:
+        from deeptreeattention_b200.train import GraphedFusedTrainStep, fused_train_step
+
+        def train_step(xd, yd=None):
+            loss = fused_train_step(model, xd, y_dev if yd is None else yd)
+            sync.sync()
+            return loss
+    else:
+        def train_step(xd, yd=None):
+            for p in params:
+                p.grad = None
+            loss = loss_fn(model, model(xd), y_dev if yd is None else yd)
+            loss.backward()
+            sync.sync()
+            return loss
 
     step_fn = train_step
     graphed = None
     if args.graph:
         from deeptreeattention_b200.graph import GraphedTrainStep
-        graphed = GraphedTrainStep(model, x_dev, y_dev, loss_fn, after_backward=sync.sync)
+        if use_fused:
+            graphed = GraphedFusedTrainStep(model, x_dev, y_dev, after_backward=sync.sync)
+        else:
+            graphed = GraphedTrainStep(model, x_dev, y_dev, loss_fn, after_backward=sync.sync)
 
         def step_fn(xd, yd=None):
             return graphed(xd, yd)
@@ -634,7 +650,10 @@ def run_b200(args):
     adam_ms = None
     if args.graph and world == 1 and args.config == "cfg3":       # N = 1 only
         opt = FusedAdam(model.parameters(), lr=1e-4, capturable=True)
-        graphed_opt = GraphedTrainStep(model, x_dev, y_dev, loss_fn, after_backward=sync.sync, optimizer=opt)
+        if use_fused:
+            graphed_opt = GraphedFusedTrainStep(model, x_dev, y_dev, after_backward=sync.sync, optimizer=opt)
+        else:
+            graphed_opt = GraphedTrainStep(model, x_dev, y_dev, loss_fn, after_backward=sync.sync, optimizer=opt)
         for _ in range(3):
             graphed_opt(x_dev)
         barrier(); torch.cuda.synchronize()
@@ -759,7 +778,9 @@ def run_b200(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": workload_string(args, world), "name": args.config,
-                   "regime": args.regime, "launch": "cuda-graph replay" if args.graph else "eager", "batch_per_gpu": B, "global_batch": B * world,
+                   "regime": args.regime, "launch": "cuda-graph replay" if args.graph else "eager",
+                   "step": "one dta_train_step call (train.fused_train_step)" if use_fused else "model(x) -> cross_entropy_heads -> backward() through autograd",
+                   "batch_per_gpu": B, "global_batch": B * world,
                    "side_stream_overlap": int(args.overlap), "programmatic_dependent_launch": bool(args.pdl), "parallelism": f"dp{world}", "gradient_exchange": sync.last_path if world > 1 else None, "l2": f"crops per step = {crops_bytes / 1e6:.0f} MB > 126 MB L2 (no flush needed)" if flush is None
                    else f"crops per step = {crops_bytes / 1e6:.0f} MB < 126 MB L2: a 256 MB write flushes L2 before every timed step (per-step events, flush not timed)",
                    "host_affinity": affinity},
@@ -768,7 +789,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "pcie_gbs_per_gpu": pcie_gbs,
                 "how": "pinned host crops + labels" + (" + site ids" if site_pin is not None else "") +
-                       " -> double-buffered H2D on a copy stream -> model(x) -> CE -> backward -> loss.item(); fp32 crops make this "
+                       " -> double-buffered H2D on a copy stream -> the same training step -> loss.item(); fp32 crops make this "
                        "PCIe-bound: pcie_gbs_per_gpu is the achieved host->device rate (PCIe 5 x16 delivers ~55-57 of its 64 GB/s)"},
         "e2e_raw_int16": {"value": e2e_raw_value, "unit": UNIT, "h2d_bytes_per_step": raw_buf[0].numel() * 2 + y_dev.numel() * 8, "d2h_bytes_per_step": 4,
                           "how": "second e2e figure (tests/test_preprocess.py: bit-identical to the sklearn path): raw int16 crops + labels from "
@@ -798,6 +819,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--graph", type=int, default=1, help="1: replay the step as one CUDA graph (default), 0: eager launches")
     ap.add_argument("--pdl", type=int, default=1, help="library option \"pdl\": 1 = programmatic dependent launch between kernels (default)")
+    ap.add_argument("--step", default="fused", choices=["fused", "autograd"],
+                    help="fused: one dta_train_step call per step where the loss is the sum over the network's heads (default); "
+                         "autograd: model(x), cross_entropy_heads, loss.backward() through torch.autograd")
     ap.add_argument("--overlap", type=int, default=2,
                     help="library option \"overlap\": 0 = caller's stream only, 1 = one side stream, 2 = + auxiliary stream (default)")
     args = ap.parse_args()

@@ -237,6 +237,14 @@ class _FusedNet(Module):
         if x.dim() != 4 or x.shape[1] != self._bands or x.shape[2] != 11 or x.shape[3] != 11:
             raise ValueError(f"expected crops of shape (B, {self._bands}, 11, 11), got {tuple(x.shape)}")
         x = x.contiguous()
+        names, params, buffers, spec = self._call_cache()
+        spec.grad_buffers = self.__dict__.get("_grad_buffers")
+        if params[0].device != x.device:
+            raise RuntimeError(f"parameter on {params[0].device} but crops on {x.device}")
+        return _FusedNetFunction.apply(x, spec, self.training, names, buffers, *params)
+
+    def _call_cache(self):
+        """(names, parameters, buffers, spec) of this module as the library sees it, rebuilt when the module tree changed."""
         # the cached name/tensor lists are valid only while no parameter, buffer or sub-module has been (re)registered
         ident = _STRUCTURE_VERSION[0]
         cache = self.__dict__.get("_fused_cache")
@@ -258,11 +266,7 @@ class _FusedNet(Module):
             self._classes = int(head.shape[0])
             cache = (names, params, buffers, _NetSpec(self._net_kind, self._bands, self._classes), ident)
             self.__dict__["_fused_cache"] = cache
-        names, params, buffers, spec = cache[:4]
-        spec.grad_buffers = self.__dict__.get("_grad_buffers")
-        if params[0].device != x.device:
-            raise RuntimeError(f"parameter on {params[0].device} but crops on {x.device}")
-        return _FusedNetFunction.apply(x, spec, self.training, names, buffers, *params)
+        return cache[:4]
 
     def _apply(self, fn, *args, **kwargs):
         self.__dict__.pop("_fused_cache", None)      # .cuda()/.to() replace buffers (and maybe parameters)
@@ -279,6 +283,8 @@ class _FusedNet(Module):
         state.pop("_fused_cache", None)
         state.pop("_grad_buffers", None)
         state.pop("head_scores", None)     # last call's outputs (autograd graph attached): not part of the module's state
+        for k in ("head_losses", "joint_scores", "_train_step_keepalive"):
+            state.pop(k, None)
         return state
 
     def fused_spec(self):

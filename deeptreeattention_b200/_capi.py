@@ -77,7 +77,7 @@ EXPORTS = ["dta_abi_version", "dta_create", "dta_destroy", "dta_last_error", "dt
            "dta_plane_mean", "dta_plane_mean_backward", "dta_conv_module_workspace_bytes", "dta_conv_module_forward",
            "dta_conv_module_backward", "dta_attention_sizes", "dta_attention_forward", "dta_attention_backward",
            "dta_classifier_forward", "dta_classifier_backward", "dta_adam_step", "dta_forward_pair", "dta_crops_nonzero",
-           "dta_ensemble_mean", "dta_metadata_sizes", "dta_metadata_forward", "dta_metadata_backward", "dta_set_grad_exchange", "dta_set_update_gate"]
+           "dta_ensemble_mean", "dta_metadata_sizes", "dta_metadata_forward", "dta_metadata_backward", "dta_set_grad_exchange", "dta_set_update_gate", "dta_train_step"]
 
 
 def sources():
@@ -161,6 +161,10 @@ def lib():
                                    C.POINTER(C.c_void_p * 6), C.c_void_p, C.POINTER(Tensors), C.c_void_p,
                                    C.c_void_p, C.c_void_p]
         L.dta_backward.restype = C.c_int
+        L.dta_train_step.argtypes = [C.c_void_p, C.POINTER(Shape), C.c_void_p, C.POINTER(Tensors), C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_void_p * 6), C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p * 6),
+                                     C.POINTER(Tensors), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.dta_train_step.restype = C.c_int
         L.dta_loss_workspace_bytes.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.dta_loss_workspace_bytes.restype = C.c_int
         L.dta_cross_entropy_heads.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p * 8), C.c_void_p,

@@ -547,7 +547,7 @@ int dta_saved_region(const dta_shape* shape, int block, int region, size_t* offs
 
 // Shared body of dta_forward and dta_forward_pair (classes_second > 0: branch 1's heads have that many classes).
 static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second, const float* x, const dta_tensors* params,
-                        float* const scores[6], float* joint, void* saved, void* workspace, void* cuda_stream) {
+                        float* const scores[6], float* joint, void* saved, void* workspace, void* cuda_stream, bool joint_optional = false) {
   NetDesc d;
   int rc = check_shape(ctx, shape, &d);
   if (rc != DTA_OK) return rc;
@@ -558,7 +558,7 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
   if (rc != DTA_OK) return rc;
   for (int h = 0; h < d.n_heads; ++h)
     if (!scores[h]) return fail(ctx, DTA_ERR_INVALID_ARG, "scores[h] is NULL for an existing head");
-  if (shape->net_kind == DTA_NET_HANG2020 && !joint) return fail(ctx, DTA_ERR_INVALID_ARG, "joint is NULL");
+  if (shape->net_kind == DTA_NET_HANG2020 && !joint && !joint_optional) return fail(ctx, DTA_ERR_INVALID_ARG, "joint is NULL");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
   cudaGetLastError();
@@ -737,7 +737,7 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
     DTA_CHECK_LAUNCH(ctx, "attn_fwd<3>");
   }
   // 5. alpha blend + copies of the last-head scores for dalpha
-  if (shape->net_kind == DTA_NET_HANG2020) {
+  if (shape->net_kind == DTA_NET_HANG2020 && joint != nullptr) {
     StageScope sc(ctx, "fwd.joint", st);
     const size_t n = (size_t)B * classes;
     launch_k(joint_fwd_kernel, (int)((n + 255) / 256), 256, 0, st, scores[2], scores[5], params->alpha, joint, L.s3[0], L.s3[1], n);
@@ -871,9 +871,11 @@ int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, c
   return DTA_OK;
 }
 
-int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_tensors* params,
-                 const void* saved, const float* const dscores[6], const float* djoint,
-                 const dta_tensors* grads, float* dx, void* workspace, void* cuda_stream) {
+// ce3: fused training step -- the score gradients of block 3's heads are formed inside its attention-backward kernel from
+// the scores (the loss kernel that writes all of dscores runs on the side stream and is joined before block 2 reads them).
+static int backward_impl(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_tensors* params,
+                         const void* saved, const float* const dscores[6], const float* djoint,
+                         const dta_tensors* grads, float* dx, void* workspace, void* cuda_stream, const CeInline* ce3) {
   NetDesc d;
   int rc = check_shape(ctx, shape, &d);
   if (rc != DTA_OK) return rc;
@@ -939,7 +941,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
       DTA_CHECK_LAUNCH(ctx, "alpha_grad");
     }
   } else if (hang && grads->alpha) {
-    cudaMemsetAsync(grads->alpha, 0, sizeof(double), st);
+    cudaMemsetAsync(grads->alpha, 0, sizeof(double), ss);   // off the critical path like every other zero-fill
   }
   auto head_ds = [&](int g, int k) -> const float* {
     if (vanilla) return k == 2 ? dS[0] : nullptr;
@@ -1078,7 +1080,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn3", st);
     launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[2], L.bn_scale[2], L.bn_shift[2], L.bn_mean[2], L.bn_istd[2], attn_prm(2), classes, L.att[2], L.feat[2],
-                                              ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow[2], tcp ? 1 : 0);
+                                              ds_ptrs(2), nullptr, W.da[2], W.bnrows, W.prow[2], tcp ? 1 : 0, ce3 ? *ce3 : CeInline{});
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<3>");
     if ((rc = attn_param_grads(2)) != DTA_OK) return rc;
@@ -1111,13 +1113,17 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     }
   }
   // ---- block 2 ----
+  if (ce3 != nullptr && aux.on) {   // fused training step: the loss kernel on the auxiliary stream has written dscores by now
+    aux.pending = true;
+    aux.join();
+  }
   {
     auto kern = attn_bwd_kernel<64, 11, true>;
     const size_t sm = attn_bwd_smem<64, 11, true>(classes);
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn2", st);
     launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[1], L.bn_scale[1], L.bn_shift[1], L.bn_mean[1], L.bn_istd[1], attn_prm(1), classes, L.att[1], L.feat[1],
-                                              ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow[1], tcp ? 1 : 0);
+                                              ds_ptrs(1), W.dout[1], W.da[1], W.bnrows, W.prow[1], tcp ? 1 : 0, CeInline{});
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<2>");
     if ((rc = attn_param_grads(1)) != DTA_OK) return rc;
@@ -1155,7 +1161,7 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
     allow_smem(kern, sm);
     StageScope asc(ctx, "bwd.attn1", st);
     launch_k(kern, dim3(B, nb), kAttnThreads, sm, st, L.z[0], L.bn_scale[0], L.bn_shift[0], L.bn_mean[0], L.bn_istd[0], attn_prm(0), classes, L.att[0], L.feat[0],
-                                              ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow[0], 0);
+                                              ds_ptrs(0), W.dout[0], W.da[0], W.bnrows, W.prow[0], 0, CeInline{});
     asc.end();
     DTA_CHECK_LAUNCH(ctx, "attn_bwd<1>");
     if ((rc = attn_param_grads(0)) != DTA_OK) return rc;
@@ -1229,6 +1235,76 @@ int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, std::string("backward: ") + cudaGetErrorString(e));
   return DTA_OK;
+}
+
+int dta_backward(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_tensors* params,
+                 const void* saved, const float* const dscores[6], const float* djoint,
+                 const dta_tensors* grads, float* dx, void* workspace, void* cuda_stream) {
+  return backward_impl(ctx, shape, x, params, saved, dscores, djoint, grads, dx, workspace, cuda_stream, nullptr);
+}
+
+// Forward + loss (sum over the heads of the weighted cross-entropy) + backward as ONE call.  Same kernels and the same bits
+// as dta_forward, dta_cross_entropy_heads(all heads), dta_backward(dscores, djoint = NULL) in sequence; what changes is the
+// schedule: the loss kernel (losses + every head's score gradient in memory) runs on the side stream, and block 3's
+// attention-backward kernel -- the next kernel of the critical chain -- forms its two heads' score gradients itself from the
+// scores, so neither the loss kernel nor the alpha blend sits between the forward and the backward pass.
+int dta_train_step(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_tensors* params, const int64_t* labels,
+                   const float* class_weight, float* const scores[6], float* joint, float* loss, float* const dscores[6],
+                   const dta_tensors* grads, void* saved, void* workspace_fwd, void* workspace_bwd, void* workspace_loss,
+                   void* cuda_stream) {
+  NetDesc d;
+  int rc = check_shape(ctx, shape, &d);
+  if (rc != DTA_OK) return rc;
+  if (shape->net_kind == DTA_NET_SPECTRAL_PAIR || shape->net_kind == DTA_NET_SPATIAL_PAIR)
+    return fail(ctx, DTA_ERR_UNSUPPORTED, "pair kinds are inference fan-out only: no training step");
+  if (!labels || !loss || !dscores || !workspace_loss || !scores) return fail(ctx, DTA_ERR_INVALID_ARG, "labels, scores, loss, dscores and workspace_loss are required");
+  if (reinterpret_cast<uintptr_t>(workspace_loss) & 255u) return fail(ctx, DTA_ERR_INVALID_ARG, "workspace_loss must be 256-byte aligned");
+  for (int h = 0; h < d.n_heads; ++h)
+    if (!dscores[h]) return fail(ctx, DTA_ERR_INVALID_ARG, "dscores[h] is NULL for an existing head");
+  if (!ctx->tickets) return fail(ctx, DTA_ERR_CUDA, "context has no ticket counters (allocation failed at dta_create)");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "cudaSetDevice failed");
+  pdl_enabled() = ctx->pdl;
+  const int B = shape->batch, classes = shape->classes;
+  double* den = reinterpret_cast<double*>(workspace_loss);                      // first 256 bytes of the loss workspace
+  float* rows = reinterpret_cast<float*>(static_cast<char*>(workspace_loss) + 256);
+  const long long* y = reinterpret_cast<const long long*>(labels);
+  long long extra_launches = 0;
+  {
+    // sum of the label weights: beside the forward pass (its side stream is joined in front of block 1's attention kernel)
+    SideStream pre(ctx, st);
+    pre.wait_main();
+    launch_k(ce_den_kernel, 1, 256, 0, pre.stream(), y, class_weight, B, classes, den);
+    if (cudaGetLastError() != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "ce_den launch failed");
+    ++extra_launches;
+    pre.pending = false;   // joined by forward_impl's own join of the same stream
+  }
+  rc = forward_impl(ctx, shape, 0, x, params, scores, joint, saved, workspace_fwd, cuda_stream, true);
+  if (rc != DTA_OK) return rc;
+  {
+    // losses and all score gradients, off the critical path: on the auxiliary stream (idle until the end of the backward
+    // pass; the side stream is busy with the backward pass's parameter tables), joined by backward_impl in front of block 2's
+    // attention kernel, the first reader of the gradients in memory
+    SideStream post(ctx, st, 1);
+    post.wait_main();
+    HeadPtrs h{};
+    for (int i = 0; i < d.n_heads; ++i) { h.s[i] = scores[i]; h.ds[i] = dscores[i]; }
+    StageScope sc(ctx, "loss.cross_entropy", post.stream());
+    launch_k(ce_rows_kernel, (unsigned)(((long long)d.n_heads * B * 32 + 255) / 256), 256, 0, post.stream(), h, d.n_heads, y, class_weight, B, classes, rows, loss,
+             ctx->tickets + 0);
+    if (cudaGetLastError() != cudaSuccess) return fail(ctx, DTA_ERR_CUDA, "ce_rows launch failed");
+    ++extra_launches;
+    if (post.on) post.pending = false;   // joined by backward_impl (same stream), not here
+  }
+  CeInline ce{};
+  const float* ds_const[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  for (int h = 0; h < d.n_heads; ++h) ds_const[h] = dscores[h];
+  const bool vanilla = shape->net_kind == DTA_NET_VANILLA;
+  for (int g = 0; g < d.nb; ++g) ce.scores[g] = vanilla ? scores[0] : scores[g * 3 + 2];
+  ce.y = y; ce.w = class_weight; ce.den = den;
+  rc = backward_impl(ctx, shape, x, params, saved, ds_const, nullptr, grads, nullptr, workspace_bwd, cuda_stream, &ce);
+  ctx->launches += extra_launches;
+  return rc;
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 // spectral_attention.forward :149-168, spatial_attention.forward :105-124, Classifier :63-66.
 #pragma once
 #include "dta_common.cuh"
+#include "dta_loss.cuh"
 #include "dta_tc.cuh"
 
 namespace dta {
@@ -379,7 +380,8 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
                 const float* __restrict__ att, const float* __restrict__ feat_unused,
                 Ptr2 dscores /*per branch [B][classes] or null*/, const float* __restrict__ dout /*[B][G][C][HW] or null*/,
                 float* __restrict__ da /*[B][G*C][HWPRE]; compact: [B][G*C][HW] values, then [B][G*C][HW] arg-max bytes*/,
-                float* __restrict__ bnrow /*[B][G][2C]*/, float* __restrict__ prow /*[B][G][ROW_LD]*/, int compact) {
+                float* __restrict__ bnrow /*[B][G][2C]*/, float* __restrict__ prow /*[B][G][ROW_LD]*/, int compact,
+                CeInline ce /*scores[g] != null: this head's score gradient is formed here from the scores (fused training step)*/) {
   pdl_prologue();
   using Cfg = AttnCfg<C, SPRE, POOL>;
   using Row = AttnBwdRow<C, SPRE, POOL>;
@@ -410,9 +412,16 @@ attn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ scale, co
   const float* att_row = att + ((size_t)b * G + g) * Cfg::ATT_LD;
   for (int i = tid; i < 3 * Cfg::ROW; i += kAttnThreads) s_v[i] = __ldg(att_row + i);
   const float* dsc = dscores.p[g];
-  const bool has_head = (dsc != nullptr) && (prm.fc_w[g] != nullptr);
-  if (has_head)
+  const bool ce_here = ce.scores[g] != nullptr;
+  const bool has_head = (dsc != nullptr || ce_here) && (prm.fc_w[g] != nullptr);
+  if (has_head && ce_here) {
+    // fused training step: the weighted cross-entropy gradient of this crop's head, by warp 0, with the arithmetic of
+    // ce_rows_kernel (which writes the same values to memory off the critical path for the head's weight gradient)
+    if (warp == 0)
+      ce_row_warp(ce.scores[g] + (size_t)b * classes, classes, ce.y[b], ce.w, ce.den[0], true, [&](int c, float v) { s_ds[c] = v; });
+  } else if (has_head) {
     for (int i = tid; i < classes; i += kAttnThreads) s_ds[i] = __ldg(dsc + (size_t)b * classes + i);
+  }
   if (!POOL) attn_stage_in(&stage_bar, s_r, zg, C * HWPRE, s_D, dsrc, C * HW);
   else if (dsrc != nullptr) attn_stage_in(&stage_bar, s_D, dsrc, C * HW, nullptr, nullptr, 0);
   build_r<C, SPRE, POOL>(zg, sc, sh, s_r, POOL ? s_arg : nullptr, POOL ? s_zarg : nullptr);   // ends with a barrier

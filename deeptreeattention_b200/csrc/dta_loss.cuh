@@ -29,9 +29,44 @@ __device__ __forceinline__ double ce_den_block(const long long* __restrict__ y, 
   return t;
 }
 
-// One warp per (head, crop): stable log-softmax, weighted NLL term and the score gradient.  The CTA that finishes LAST
-// (ticket counter in context-owned memory, reset by that CTA) also sums the rows into the losses -- fixed order, fp64 -- so the
-// loss costs one launch on the step's critical path instead of two.
+// One warp: stable log-softmax of one score row, its weighted NLL term (returned in every lane) and, through emit(c, v), the
+// gradient of  sum_b w[y_b] nll_b / dsum  with respect to the row.  Shared by ce_rows_kernel and by the attention-backward
+// kernel of a fused training step (dta_train_step), which therefore produce the same bits.
+template <class Emit>
+__device__ __forceinline__ float ce_row_warp(const float* __restrict__ s, int classes, long long yc, const float* __restrict__ w,
+                                             double dsum, bool want_grad, Emit emit) {
+  const int lane = threadIdx.x & 31;
+  float m = -INFINITY;
+  for (int c = lane; c < classes; c += 32) m = fmaxf(m, __ldg(s + c));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float z = 0.f;
+  for (int c = lane; c < classes; c += 32) z = __fadd_rn(z, expf(__fsub_rn(__ldg(s + c), m)));
+  z = warp_sum(z);
+  const bool ok = yc >= 0 && yc < classes;
+  const float wy = ok ? (w ? __ldg(w + yc) : 1.f) : 0.f;
+  const float lse = __fadd_rn(m, logf(z));
+  if (want_grad) {
+    const float k = __fmul_rn(wy, (float)(1.0 / dsum));
+    for (int c = lane; c < classes; c += 32) {
+      const float p = expf(__fsub_rn(__ldg(s + c), lse));
+      emit(c, __fmul_rn(k, __fsub_rn(p, c == yc ? 1.f : 0.f)));
+    }
+  }
+  return ok ? __fmul_rn(wy, __fsub_rn(lse, __ldg(s + yc))) : 0.f;
+}
+
+// den = sum_b w[y_b] as its own (one-CTA) launch: a fused training step computes it beside the forward pass so that the
+// attention-backward kernel of block 3 can form its heads' score gradients itself.  Same bits as ce_den_block anywhere else.
+__global__ void __launch_bounds__(256) ce_den_kernel(const long long* __restrict__ y, const float* __restrict__ w, int B, int classes, double* __restrict__ den) {
+  pdl_prologue();
+  __shared__ double s_red[8];
+  const double d = ce_den_block(y, w, B, classes, s_red);
+  if (threadIdx.x == 0) den[0] = d;
+}
+
+// One warp per (head, crop).  The CTA that finishes LAST (ticket counter in context-owned memory, reset by that CTA) also sums
+// the rows into the losses -- fixed order, fp64 -- so the loss costs one launch on the step's critical path instead of two.
 __global__ void __launch_bounds__(256)
 ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restrict__ y, const float* __restrict__ w, int B, int classes,
                float* __restrict__ row_loss /*[n_heads][B]*/, float* __restrict__ loss /*[n_heads + 1]*/, unsigned int* __restrict__ ticket) {
@@ -42,28 +77,11 @@ ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restrict__ y, const f
   const double dsum = ce_den_block(y, w, B, classes, s_red);
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw < n_heads * B) {
-  const int head = gw / B, b = gw - head * B;
-  const float* s = h.s[head] + (size_t)b * classes;
-  float m = -INFINITY;
-  for (int c = lane; c < classes; c += 32) m = fmaxf(m, __ldg(s + c));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  float z = 0.f;
-  for (int c = lane; c < classes; c += 32) z += expf(__ldg(s + c) - m);
-  z = warp_sum(z);
-  const long long yc = y[b];
-  const bool ok = yc >= 0 && yc < classes;
-  const float wy = ok ? (w ? __ldg(w + yc) : 1.f) : 0.f;
-  const float lse = m + logf(z);
-  if (lane == 0) row_loss[(size_t)head * B + b] = ok ? wy * (lse - __ldg(s + yc)) : 0.f;
-  float* ds = h.ds[head];
-  if (ds != nullptr) {
-    const float inv = (float)(1.0 / dsum);
-    for (int c = lane; c < classes; c += 32) {
-      const float p = expf(__ldg(s + c) - lse);
-      ds[(size_t)b * classes + c] = wy * inv * (p - (c == yc ? 1.f : 0.f));
-    }
-  }
+    const int head = gw / B, b = gw - head * B;
+    float* ds = h.ds[head];
+    const float rl = ce_row_warp(h.s[head] + (size_t)b * classes, classes, y[b], w, dsum, ds != nullptr,
+                                 [&](int c, float v) { ds[(size_t)b * classes + c] = v; });
+    if (lane == 0) row_loss[(size_t)head * B + b] = rl;
   }
   // ---- last CTA: loss[head] = sum_b row_loss / den (fp64, fixed order), loss[n_heads] = sum over heads ----
   __threadfence();
@@ -92,5 +110,14 @@ ce_rows_kernel(HeadPtrs h, int n_heads, const long long* __restrict__ y, const f
     *ticket = 0u;
   }
 }
+
+// What the attention-backward kernel needs to form its heads' score gradients from the scores themselves (fused training
+// step, block 3): scores == nullptr for a branch = read the gradient from memory as usual.
+struct CeInline {
+  const float* scores[2];     // per branch: (B, classes) scores of this block's head
+  const long long* y;         // (B) labels
+  const float* w;             // (classes) class weights or nullptr
+  const double* den;          // sum_b w[y_b] (ce_den_kernel)
+};
 
 }  // namespace dta

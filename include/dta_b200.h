@@ -221,6 +221,25 @@ int dta_cross_entropy_heads(dta_ctx* ctx, int batch, int classes, int n_heads, c
                             float* const dscores[], void* workspace, void* cuda_stream);
 
 /*
+ * One training step of the regime the north star names, in ONE call: forward, loss = sum over the network's heads of the
+ * class-weighted cross-entropy, backward.  Replaces, for a caller that sums the head losses,
+ *     y_hat = self.model.forward(images); loss = F.cross_entropy(y_hat, y, weight=self.loss_weight); loss.backward()
+ * of TreeModel.training_step (src/main.py:71-80) plus the autograd pass Lightning runs behind it.  Results are bit-identical to
+ * dta_forward + dta_cross_entropy_heads(every head) + dta_backward(dscores, djoint = NULL); only the schedule differs: the
+ * loss kernel leaves the critical path (side stream) and block 3's attention-backward kernel forms its heads' score gradients
+ * from the scores itself, so nothing sits between the last forward kernel and the first backward kernel.
+ *   labels (batch) int64, class_weight (classes) float32 or NULL; scores / joint / saved / workspace_fwd as dta_forward
+ *   (joint may be NULL: the alpha blend is skipped; alpha's gradient is zero in this regime either way)
+ *   loss      : n_heads + 1 floats, as dta_cross_entropy_heads
+ *   dscores[h]: (batch, classes) float32 per existing head, caller-owned, receives d loss / d scores[h]
+ *   grads / workspace_bwd as dta_backward;  workspace_loss : dta_loss_workspace_bytes(batch, n_heads) bytes, 256-byte aligned
+ */
+int dta_train_step(dta_ctx* ctx, const dta_shape* shape, const float* x, const dta_tensors* params,
+                   const int64_t* labels, const float* class_weight, float* const scores[6], float* joint,
+                   float* loss, float* const dscores[6], const dta_tensors* grads, void* saved,
+                   void* workspace_fwd, void* workspace_bwd, void* workspace_loss, void* cuda_stream);
+
+/*
  * Raw crown crops -> network input, on the device.  Replaces utils.preprocess_image (src/utils.py:36-57) for
  * crops that are already 11 x 11: drop `clip` bands at each end (the reference drops 10 when there are more than
  * 3 bands), cast int16 -> float32, scale every pixel's spectrum to [0, 1] with the float32 arithmetic of
