@@ -101,7 +101,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libdta_b200.so (no CPU fallback exists)")
     cu = [s for s in sources() if s.endswith(".cu")]
-    tmp = LIB_PATH + ".tmp"
+    tmp = f"{LIB_PATH}.{os.getpid()}.tmp"      # several ranks may find the binary stale at once: private output, atomic replace
     cmd = [nvcc] + NVCC_FLAGS + cu + ["-o", tmp]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -87,9 +87,28 @@ def main():
     ge = step(mp, sp, "R2+joint")
     torch.cuda.synchronize()
     worst = max(float((mg.get_parameter(k).grad - ge[k]).abs().max()) / (float(ge[k].abs().max()) + 1e-12) for k in ge)
+    # the one-call training step (train.fused_train_step, regime R2) followed by the same exchange, eager and captured,
+    # against the autograd path on the same crops
+    from deeptreeattention_b200.train import GraphedFusedTrainStep, fused_train_step
+    ma, sa = build(True)
+    for p in ma.parameters():
+        p.grad = None
+    ma(x)
+    cross_entropy_heads(ma.head_scores, y).backward()
+    sa.sync()
+    mf, sf = build(True)
+    fused_train_step(mf, x, y)
+    sf.sync()
+    mh, sh = build(True)
+    gf = GraphedFusedTrainStep(mh, x, y, after_backward=sh.sync)
+    gf()
+    torch.cuda.synchronize()
+    fused_same = all((pa.grad is None) == (pf.grad is None) and (pa.grad is None or (torch.equal(pa.grad, pf.grad) and torch.equal(pa.grad, ph.grad)))
+                     for pa, pf, ph in zip(ma.parameters(), mf.parameters(), mh.parameters()))
     if rank == 0:
         print(f"graph replay vs eager (peer path {sg.last_path}): worst relative difference {worst:.2e}", flush=True)
-        print("DIST CHECK", "OK" if ok and worst < 1e-5 else "FAILED", flush=True)
+        print(f"fused training step + exchange ({sf.last_path}) == autograd path + exchange, eager and captured, bit for bit: {fused_same}", flush=True)
+        print("DIST CHECK", "OK" if ok and worst < 1e-5 and fused_same else "FAILED", flush=True)
     sys.stdout.flush()
     torch.cuda.synchronize(); dist.barrier()
     os._exit(0)

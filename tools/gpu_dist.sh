@@ -5,7 +5,7 @@ TAG=${1:-r05}
 N=${2:-2}
 mkdir -p gpurun_out
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 300 $RUN --master-port 29511 tools/dist_check.py > gpurun_out/${TAG}_dist_check_n${N}.log 2>&1; grep -E "paths|exchange|graph replay|DIST CHECK|Error|error" gpurun_out/${TAG}_dist_check_n${N}.log | tail -8
+timeout 300 $RUN --master-port 29511 tools/dist_check.py > gpurun_out/${TAG}_dist_check_n${N}.log 2>&1; grep -E "paths|exchange|graph replay|fused|DIST CHECK|Error|error" gpurun_out/${TAG}_dist_check_n${N}.log | tail -8
 timeout 300 $RUN --master-port 29512 bench.py --gpus $N --steps 30 --warmup 5 --sustain 0 > gpurun_out/${TAG}_bench_n${N}.json 2> gpurun_out/${TAG}_bench_n${N}.err; echo "bench rc=$?"
 DTA_EXCHANGE_IN_BACKWARD=1 timeout 300 $RUN --master-port 29513 bench.py --gpus $N --steps 30 --warmup 5 --sustain 0 > gpurun_out/${TAG}_bench_n${N}_inbackward.json 2>> gpurun_out/${TAG}_bench_n${N}.err; echo "bench(exchange in backward) rc=$?"
 timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu --sustain 0 > gpurun_out/${TAG}_bench_n1.json 2>> gpurun_out/${TAG}_bench_n${N}.err
