@@ -169,11 +169,8 @@ __device__ __forceinline__ float stencil_at(const float* s_plane, const float* _
 }
 
 // ------------------------------------------------------------------------------ forward
-#ifndef DTA_ATTN_FWD_MINB
-#define DTA_ATTN_FWD_MINB 1
-#endif
 template <int C, int SPRE, bool POOL>
-__global__ void __launch_bounds__(kAttnThreads, DTA_ATTN_FWD_MINB)
+__global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const float* __restrict__ z /*[B][G*C][HWPRE]*/, const float* __restrict__ scale,
                 const float* __restrict__ shift, AttnParams prm, int classes,
                 float* __restrict__ att /*[B][G][ATT_LD]*/, float* __restrict__ feat /*[B][G][FEAT_LD]*/,
