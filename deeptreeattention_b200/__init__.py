@@ -5,6 +5,7 @@
 ``multi_stage``  ``base_model`` and the arithmetic of ``MultiStage.predict_step`` (``src.models.multi_stage``)
 ``metadata``     ``src.models.metadata`` (site MLP + fusion around the CUDA Hang2020)
 ``loss``         fused weighted cross-entropy over the heads (``TreeModel.training_step``'s loss line)
+``train``        forward + summed head losses + backward as ONE library call (``TreeModel.training_step`` + ``backward()``)
 ``optim``        ``FusedAdam``: the optimizer the reference configures, one launch per step
 ``data``         int16 crop preprocessing on the device (``utils.preprocess_image``)
 ``graph``        CUDA-graph capture of a whole training step
@@ -16,5 +17,5 @@ Sub-modules other than ``Hang2020`` and ``_capi`` are imported on demand (``from
 from . import _capi  # noqa: F401
 from . import Hang2020  # noqa: F401
 
-__all__ = ["Hang2020", "_capi", "year", "multi_stage", "metadata", "loss", "optim", "data", "graph", "distributed"]
+__all__ = ["Hang2020", "_capi", "year", "multi_stage", "metadata", "loss", "train", "optim", "data", "graph", "distributed"]
 __version__ = "0.2.0"

@@ -148,6 +148,18 @@ def test_year_and_metadata_modules_mirror_the_reference_surface():
         f(torch.randn(2, 3, 11, 11), torch.zeros(2).int())
 
 
+def test_fused_train_step_host_side_errors():
+    """train.fused_train_step checks its arguments on the host before any library call: no CPU path, fused networks only."""
+    import torch
+    from deeptreeattention_b200 import Hang2020 as H
+    from deeptreeattention_b200.train import fused_train_step
+    m = H.spectral_network(12, 4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fused_train_step(m, torch.zeros(2, 12, 11, 11), torch.zeros(2, dtype=torch.int64))
+    with pytest.raises(TypeError):
+        fused_train_step(torch.nn.Linear(3, 3), torch.zeros(2, 12, 11, 11), torch.zeros(2, dtype=torch.int64))
+
+
 def test_product_code_never_touches_the_oracle_or_a_cpu_fallback():
     """The oracle is test infrastructure: nothing under deeptreeattention_b200/ may import it, and no product module may
     import the reference tree either."""
