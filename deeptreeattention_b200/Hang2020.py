@@ -283,7 +283,7 @@ class _FusedNet(Module):
         state.pop("_fused_cache", None)
         state.pop("_grad_buffers", None)
         state.pop("head_scores", None)     # last call's outputs (autograd graph attached): not part of the module's state
-        for k in ("head_losses", "joint_scores", "_train_step_keepalive"):
+        for k in ("head_losses", "joint_scores"):
             state.pop(k, None)
         return state
 

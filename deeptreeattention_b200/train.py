@@ -98,7 +98,8 @@ def fused_train_step(model: _FusedNet, x: torch.Tensor, y: torch.Tensor, weight:
     model.head_scores = scores if spec.kind != _capi.NET_VANILLA else None
     model.head_losses = loss[:spec.n_heads]
     model.joint_scores = joint
-    model.__dict__["_train_step_keepalive"] = (saved, work_f, work_b, work_l, dscores)   # until the next step (stream-ordered reuse)
+    # saved / workspaces / dscores go back to the caching allocator here: the library joined its side streams into the caller's
+    # stream before returning, so stream-ordered reuse is safe (same as the work buffers of the autograd path)
     return loss[spec.n_heads]
 
 
