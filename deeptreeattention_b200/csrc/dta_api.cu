@@ -486,6 +486,11 @@ int dta_set_option(dta_ctx* ctx, const char* key, int64_t value) {
     ctx->profile = value != 0;
     return DTA_OK;
   }
+  if (!strcmp(key, "small_tiles")) {
+    if (value < 0 || value > 2) return fail(ctx, DTA_ERR_INVALID_ARG, "small_tiles: 0 = never, 1 = eval mode (default), 2 = training too");
+    ctx->small_tiles = (int)value;
+    return DTA_OK;
+  }
   if (!strcmp(key, "fuse_x")) {
     ctx->fuse_x = value != 0;
     return DTA_OK;
@@ -518,6 +523,7 @@ int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value) {
   if (!strcmp(key, "overlap")) { *value = ctx->overlap; return DTA_OK; }
   if (!strcmp(key, "pdl")) { *value = ctx->pdl; return DTA_OK; }
   if (!strcmp(key, "fuse_x")) { *value = ctx->fuse_x; return DTA_OK; }
+  if (!strcmp(key, "small_tiles")) { *value = ctx->small_tiles; return DTA_OK; }
   if (!strcmp(key, "exchanged")) { *value = ctx->exchanged; return DTA_OK; }
   return DTA_ERR_INVALID_ARG;
 }
@@ -632,9 +638,20 @@ static int forward_impl(dta_ctx* ctx, const dta_shape* shape, int classes_second
           cudaMemsetAsync(reinterpret_cast<char*>(L.xp) + used, 0, all - used, st);
           cudaMemsetAsync(reinterpret_cast<char*>(L.xp) + all + used, 0, all - used, st);
         }
-        DTA_TC_CHECK((run_tc_fprop<11, 64, false, true>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32,
-                                                       nb * 32, B, 1, shape->training ? W.stats : nullptr, &nblk, FuseX{x, bands, L.xp})),
-                     "tc_conv_fprop(conv1, fused crops)");
+        // 512-position tiles (one accumulator of all 512 tensor-memory columns: the weights stream half as often) while they
+        // fill the SMs; at small batches 256-position tiles (two accumulator stages) keep twice as many SMs busy
+        const bool big_tiles = (long long)(tg.rows11 - 2 * kTcGuard) / TcFprop<11, 64, false>::TILE >= (ctx->sm_count < kTcSmCount ? ctx->sm_count : kTcSmCount);
+        // (training keeps the 512-position tiles unless small_tiles = 2: the BatchNorm partial sums are grouped per CTA, so the
+        // tile size moves the batch statistics in their last bits; in eval mode the two forms are bit-identical)
+        const bool small = !big_tiles && (ctx->small_tiles == 2 || (ctx->small_tiles == 1 && !shape->training));
+        if (!small)
+          DTA_TC_CHECK((run_tc_fprop<11, 64, false, true>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32,
+                                                         nb * 32, B, 1, shape->training ? W.stats : nullptr, &nblk, FuseX{x, bands, L.xp})),
+                       "tc_conv_fprop(conv1, fused crops)");
+        else
+          DTA_TC_CHECK((run_tc_fprop<11, 64, true, true>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32,
+                                                        nb * 32, B, 1, shape->training ? W.stats : nullptr, &nblk, FuseX{x, bands, L.xp})),
+                       "tc_conv_fprop(conv1, fused crops, 256-position tiles)");
       } else {
         DTA_TC_CHECK((run_tc_fprop<11, 64, false>(ctx, st, L.xp, tg.rows11, tg.nchunk1, 0, W.wpf[0], tg.nstage1, conv_b(0), 32, L.z[0], nb * 32, nb * 32, B, 1,
                                                  shape->training ? W.stats : nullptr, &nblk)),

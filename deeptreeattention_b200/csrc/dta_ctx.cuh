@@ -23,6 +23,10 @@ struct dta_ctx {
   long long launches_total = 0;   // ... by all earlier calls on this context (option "launches_total" = both)
   int profile = 0;
   int fuse_x = 1;      // conv1 forward converts the raw crops itself (no separate pack pass); 0 = pack kernel + pre-packed operand
+#ifndef DTA_SMALL_TILES_DEFAULT
+#define DTA_SMALL_TILES_DEFAULT 1
+#endif
+  int small_tiles = DTA_SMALL_TILES_DEFAULT;   // conv1 forward (fused crops): 256-position tiles when 512-position ones would leave SMs idle (small batches): 0 never, 1 eval mode, 2 training too
   std::vector<std::string> stage_names;
   std::vector<double> stage_ms;
   std::vector<long long> stage_calls;
