@@ -130,7 +130,12 @@ const char* dta_last_error(const dta_ctx* ctx); /* ctx may be NULL: last create 
  * small-parameter reduction does not queue between two weight gradients; 0 = everything on the caller's stream.
  * key "pdl": 1 (default) = consecutive kernels of a call are launched with programmatic dependent launch (the next kernel's
  * CTAs are scheduled while the previous grid drains and wait for its completion before touching memory): same stream order,
- * less launch latency between the ~60 short kernels of a step; 0 = plain launches. */
+ * less launch latency between the ~60 short kernels of a step; 0 = plain launches.
+ * key "fuse_x": 1 (default) = conv1's forward kernel converts the raw float32 crops into its split-bf16 operand itself (and
+ * leaves the packed copy the weight gradient reads); 0 = a separate pack pass in front.  Same bits either way.
+ * key "small_tiles": conv1 forward at batches whose 512-position tiles would leave SMs idle (< ~526 crops): 256-position tiles
+ * and two accumulator stages.  1 (default) = in eval mode (bit-identical there), 2 = in training too (the per-CTA grouping
+ * of the BatchNorm partial sums then moves the batch statistics in their last bits), 0 = never. */
 int dta_set_option(dta_ctx* ctx, const char* key, int64_t value);
 int dta_get_option(const dta_ctx* ctx, const char* key, int64_t* value);
 
