@@ -2,7 +2,10 @@
 // launch sequences (see include/dta_b200.h for the contract and DESIGN.md for the plan).
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "dta_attention.cuh"
@@ -244,9 +247,20 @@ int check_shape(dta_ctx* ctx, const dta_shape* s, NetDesc* d) {
   return DTA_OK;
 }
 
+// Opt a kernel in to `bytes` of dynamic shared memory -- once per (device, kernel, size), not on every launch.
 template <typename K>
 cudaError_t allow_smem(K kernel, size_t bytes) {
-  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const std::pair<int, const void*> key(dev, reinterpret_cast<const void*>(kernel));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) done[key] = bytes;
+  return e;
 }
 
 // ---- convolution launchers (conv_impl 0) ----------------------------------------------
