@@ -26,7 +26,9 @@ def fused_train_step(model: _FusedNet, x: torch.Tensor, y: torch.Tensor, weight:
     """Forward + summed weighted cross-entropy over every head + backward of a fused network (``Hang2020``,
     ``spectral_network``, ``spatial_network``, ``vanilla_CNN``).  Returns the loss (0-dim tensor, detached); sets ``p.grad`` of
     every parameter (``None`` for ``alpha``, which this loss does not reach, like autograd) and ``model.head_scores`` /
-    ``model.head_losses``.  ``want_joint``: also compute ``Hang2020``'s blended scores (``model.joint_scores``)."""
+    ``model.head_losses``.  ``want_joint``: also compute ``Hang2020``'s blended scores (``model.joint_scores``).
+    Gradients are OVERWRITTEN, not accumulated (the step is ``p.grad = None; ...; loss.backward()`` in one call): for
+    gradient accumulation over micro-batches use the autograd path (``model(x)`` / ``cross_entropy_heads`` / ``backward()``)."""
     if not isinstance(model, _FusedNet):
         raise TypeError("fused_train_step needs one of the fused networks of deeptreeattention_b200.Hang2020")
     if not x.is_cuda:
